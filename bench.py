@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- sample points evaluated + classified per second (BASELINE.json's metric).
+
+Workload (config 5 of BASELINE.json, the one the metric's 1/2/4/8-GPU sweep is quoted on):
+Styblinski-Tang 8-D on [-5,5]^8, unscrambled Sobol indices [0, n), n = 2^28 by default, classified
+on the SYNTHETIC index-hypercube CSR of BASELINE.md section 5 (vertex i ~ i XOR 2^j, degree
+log2 n; explicit int64 row_ptr / int32 col).  THIS IS NOT A DELAUNAY GRAPH: qhull cannot produce
+one at this size; parity on real qhull graphs is covered by tests/.
+
+One step = one shgo iteration of the hot path: fused generate->scale->evaluate->mask (K1+K2),
+[exchange of f between ranks], CSR star test (K4), pool compaction, nfev count.
+Strong scaling: n is fixed, rank r owns Sobol indices / CSR rows [r n/N, (r+1) n/N).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log2n 28] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D = 8
+BOUNDS = [(-5.0, 5.0)] * D
+FUNCTOR = "styblinski_tang"
+FLOPS_PER_POINT = 2 * D + 7 * D + 1      # scaling 2d + functor 7d+1
+KERNELS_PER_STEP = 6                      # eval, star, 3x compaction, nfev
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=28, help="log2 of the total number of points")
+    ap.add_argument("--e2e-log2n", type=int, default=26, help="log2 n of the host-buffer (e2e) leg")
+    ap.add_argument("--cpu-log2n", type=int, default=24, help="log2 n of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference itself is per-vertex Python at ~1.5e4 points/s and
+# cannot build this graph) on all host threads, bounded sample.
+# ----------------------------------------------------------------------------------------------
+def cpu_run(log2n, repeats):
+    import numpy as np
+    from oracle import oracle as orc
+    n = 1 << log2n
+    b = np.array(BOUNDS)
+    sv = orc.sobol_dirnums(D)
+    rp, col = orc.hypercube_csr(n)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        f, feas = orc.sobol_eval(sv, FUNCTOR, None, 0, n, b[:, 0], b[:, 1])
+        is_min = orc.star_csr(rp, col, f)
+        pool = orc.compact_pool(is_min)
+        nfev = orc.nfev(rp, feas)
+        times.append(time.perf_counter() - t0)
+    return n, times, len(pool), nfev, orc.num_threads()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, times, npool, nfev, cores = cpu_run(args.cpu_log2n, args.warmup + args.steps)
+    t = times[args.warmup:]
+    ms = 1e3 * sum(t) / len(t)
+    val = n / (ms * 1e-3)
+    sample = ("oracle C port (oracle/shgo_oracle.c, OpenMP) of the same step on 2^%d points; the "
+              "Python reference itself runs ~1.5e4 points/s (BASELINE.md)" % args.cpu_log2n)
+    print(json.dumps({
+        "impl": "reference", "metric": "sample points evaluated+classified/sec", "value": val,
+        "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.cpu_log2n), "points": n},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(log2n):
+    return ("cfg5: Styblinski-Tang 8-D [-5,5]^8, Sobol n=2^%d, synthetic index-hypercube CSR "
+            "(degree %d, not Delaunay)" % (log2n, log2n))
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from shgo_b200 import functors as F
+    from shgo_b200 import hotpath as hp
+    from shgo_b200 import _lib
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA devices; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+
+    n = 1 << args.log2n
+    m = args.log2n
+    assert n % world == 0
+    rows = n // world
+    row0 = rank * rows
+    fid = F.F_STYBLINSKI_TANG
+    tab = hp.SobolTables(BOUNDS, dev)
+
+    # ---- graph shard (inputs resident in HBM before the timed region) -----------------------
+    row_ptr_l = torch.arange(row0 * m, (row0 + rows + 1) * m, m, dtype=torch.int64, device=dev)
+    col_l = torch.empty((rows, m), dtype=torch.int32, device=dev)
+    bits = (1 << torch.arange(m, dtype=torch.int32, device=dev))[None, :]
+    for s in range(0, rows, 1 << 22):
+        e = min(rows, s + (1 << 22))
+        i = torch.arange(row0 + s, row0 + e, dtype=torch.int32, device=dev)[:, None]
+        torch.bitwise_xor(i, bits, out=col_l[s:e])
+    col_l = col_l.reshape(-1)
+    # the C ABI addresses the whole graph; a shard passes the virtual base of its slices
+    rp_base = row_ptr_l.data_ptr() - row0 * 8
+    col_base = col_l.data_ptr() - row0 * m * 4
+    f_all = torch.empty(n, dtype=torch.float64, device=dev)
+    f_my = f_all[row0:row0 + rows]
+    feas = torch.empty(rows, dtype=torch.uint8, device=dev)
+    is_min = torch.empty(rows, dtype=torch.uint8, device=dev)
+    work = hp.PoolWorkspace(rows, rows // 8, dev)
+    nfev = torch.zeros(1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(ev=None):
+        hp.eval_sobol(fid, F.G_NONE, tab, row0, rows, f=f_my, feasible=feas)
+        if world > 1:
+            dist.all_gather_into_tensor(f_all, f_my)
+        if ev:
+            ev[0].record(stream)
+        _lib.call("shgo_b200_star_csr", rp_base, col_base, f_all.data_ptr(), row0, rows,
+                  is_min.data_ptr(), stream.cuda_stream)
+        if ev:
+            ev[1].record(stream)
+        hp.compact_pool(is_min, base=row0, work=work)
+        _lib.call("shgo_b200_count_nfev", rp_base + row0 * 8, feas.data_ptr(), rows, nfev.data_ptr(),
+                  stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record(stream)
+    for k in range(args.steps):
+        step(evs[k])
+    t1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t0.elapsed_time(t1)
+    star_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    tt = torch.tensor([ms_total, star_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step = float(tt[0].item()) / args.steps
+    star_ms = float(tt[1].item())
+    value = n / (ms_step * 1e-3)
+    pool_count = int(work.count[0].item())
+    pc = torch.tensor([pool_count, int(nfev.item())], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(pc)
+
+    # eval kernel alone (for the FP64 side of the roofline)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(5):
+        hp.eval_sobol(fid, F.G_NONE, tab, row0, rows, f=f_my, feasible=feas)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    eval_ms = e0.elapsed_time(e1) / 5
+
+    # ---- e2e: HOST buffers through the C ABI, copies inside the timed region ------------------
+    e2e = None
+    if not args.no_e2e:
+        ne = 1 << min(args.e2e_log2n, args.log2n)
+        me = min(args.e2e_log2n, args.log2n)
+        re_ = ne // world
+        r0e = rank * re_
+        del col_l, row_ptr_l
+        torch.cuda.empty_cache()
+        rp_h = torch.arange(0, (re_ + 1) * me, me, dtype=torch.int64).pin_memory()
+        col_d = torch.empty((re_, me), dtype=torch.int32, device=dev)
+        bits = (1 << torch.arange(me, dtype=torch.int32, device=dev))[None, :]
+        for s in range(0, re_, 1 << 22):
+            e = min(re_, s + (1 << 22))
+            i = torch.arange(r0e + s, r0e + e, dtype=torch.int32, device=dev)[:, None]
+            torch.bitwise_xor(i, bits, out=col_d[s:e])
+        col_h = torch.empty(re_ * me, dtype=torch.int32).pin_memory()
+        col_h.copy_(col_d.reshape(-1))
+        del col_d
+        torch.cuda.empty_cache()
+        pool_h = torch.empty(max(re_ // 8, 1), dtype=torch.int64).pin_memory()
+        cnt, nf = ctypes.c_uint64(), ctypes.c_uint64()
+        if world == 1:
+            ctx = ctypes.c_void_p()
+            _lib.call("shgo_b200_ctx_create", local, ctypes.byref(ctx))
+            sv_h, lb_h, ub_h = tab.sv_host, tab.lb_host, tab.ub_host
+
+            def e2e_step():
+                _lib.call("shgo_b200_iterate_sobol_host", ctx, fid, F.G_NONE, D, 0, ne, sv_h.ctypes.data,
+                          lb_h.ctypes.data, ub_h.ctypes.data, rp_h.data_ptr(), col_h.data_ptr(),
+                          pool_h.data_ptr(), pool_h.numel(), ctypes.byref(cnt), ctypes.byref(nf), None)
+        else:
+            # multi-GPU: same stages, host CSR shard uploaded every step, f exchanged over NCCL
+            rp_d = torch.empty(re_ + 1, dtype=torch.int64, device=dev)
+            col_dd = torch.empty(re_ * me, dtype=torch.int32, device=dev)
+            fe_all = torch.empty(ne, dtype=torch.float64, device=dev)
+            fe_my = fe_all[r0e:r0e + re_]
+            feas_e = torch.empty(re_, dtype=torch.uint8, device=dev)
+            ismin_e = torch.empty(re_, dtype=torch.uint8, device=dev)
+            work_e = hp.PoolWorkspace(re_, pool_h.numel(), dev)
+            cnt_h = torch.zeros(2, dtype=torch.int64).pin_memory()
+
+            def e2e_step():
+                rp_d.copy_(rp_h, non_blocking=True)
+                col_dd.copy_(col_h, non_blocking=True)
+                hp.eval_sobol(fid, F.G_NONE, tab, r0e, re_, f=fe_my, feasible=feas_e)
+                dist.all_gather_into_tensor(fe_all, fe_my)
+                # local row_ptr starts at 0: virtual bases so that row r0e maps to local row 0
+                _lib.call("shgo_b200_star_csr", rp_d.data_ptr() - r0e * 8, col_dd.data_ptr(),
+                          fe_all.data_ptr(), r0e, re_, ismin_e.data_ptr(), stream.cuda_stream)
+                hp.compact_pool(ismin_e, base=r0e, work=work_e)
+                cnt_h.copy_(work_e.count, non_blocking=True)
+                torch.cuda.synchronize()
+                c = min(int(cnt_h[0]), pool_h.numel())
+                pool_h[:c].copy_(work_e.idx[:c])
+                cnt.value = int(cnt_h[0])
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        w0 = time.perf_counter()
+        ksteps = max(3, min(args.steps, 5))
+        for _ in range(ksteps):
+            e2e_step()
+        barrier()
+        wall = (time.perf_counter() - w0) / ksteps
+        wt = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        wall = float(wt.item())
+        h2d = (re_ + 1) * 8 + re_ * me * 4 + D * 30 * 4 + 2 * D * 8
+        d2h = 16 + int(cnt.value) * 8
+        e2e = {"value": ne / wall, "unit": "points/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "points": ne, "ms_per_step": wall * 1e3,
+               "note": "host CSR (pinned) uploaded, pool indices read back, every step; C-ABI "
+                       "shgo_b200_iterate_sobol_host at N=1"}
+        if world == 1:
+            _lib.lib().shgo_b200_ctx_destroy(ctx)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = peaks()
+    nnz_l = rows * m
+    alg_bytes = 4 * nnz_l + 17 * rows
+    achieved = alg_bytes / (star_ms * 1e-3) / 1e9
+    fp64_peak = hp.fp64_peak_tflops()
+    eval_tflops = FLOPS_PER_POINT * rows / (eval_ms * 1e-3) / 1e12
+    out = {
+        "metric": "sample points evaluated+classified/sec", "value": value, "unit": "points/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.log2n), "points": n, "rows_per_gpu": rows,
+                   "l2": "inputs (col = %.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
+                         % (nnz_l * 4 / 1e9),
+                   "exchange": "nccl all_gather of f" if world > 1 else "none"},
+        "roofline": {"bound": "hbm", "kernel": "star_csr_kernel", "achieved": achieved,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": star_ms},
+        "eval_kernel": {"ms_per_launch": eval_ms, "tflops_fp64_algorithmic": eval_tflops,
+                        "fp64_peak_measured_tflops": fp64_peak,
+                        "frac_fp64": eval_tflops / fp64_peak if fp64_peak else None,
+                        "hbm_write_gbs": 9 * rows / (eval_ms * 1e-3) / 1e9},
+        "pool_size": int(pc[0].item()), "nfev": int(pc[1].item()),
+        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "clocks": clocks,
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if not args.no_cpu:
+        ncpu, times, npool, nfev_c, cores = cpu_run(args.cpu_log2n, 3)
+        best = min(times)
+        out["cpu_baseline"] = {
+            "value": ncpu / best, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": "oracle C port (OpenMP, %d threads) of the same step on 2^%d points (degree "
+                      "%d graph), best of 3; the Python reference itself runs ~1.5e4 points/s "
+                      "single-core (BASELINE.md section 2)" % (cores, args.cpu_log2n, args.cpu_log2n)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,186 @@
+/*
+ * shgo_b200.h -- C ABI of the B200 (sm_100a) sampling-and-classification hot path of SHGO.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no torch / C++ types.
+ * The reference (Stefan-Endres/shgo) is pure Python and has no FFI of its own; each entry point
+ * below names the reference code it replaces (paths relative to the reference checkout) and
+ * INTEGRATION.md shows the ctypes stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - Unless a parameter is marked [host], every pointer is a DEVICE pointer owned by the
+ *     caller.  Nothing is allocated behind the caller's back except inside a shgo_b200_ctx.
+ *   - Every function enqueues on the caller's stream (`stream` is a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream) and returns immediately; results are valid
+ *     after the stream is synchronised.
+ *   - Return value: 0 on success, a SHGO_B200_ERR_* code otherwise; the message is available
+ *     from shgo_b200_last_error() (thread local).  Functions never throw and never exit.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point returns
+ *     SHGO_B200_ERR_CUDA.
+ *   - Vertex / point indices are int32 in `col` (n <= 2^31) and int64 in `row_ptr` and pools.
+ *     Sobol indices are limited to k0 + n <= 2^30 (30-bit generator, like scipy's).
+ */
+#ifndef SHGO_B200_H
+#define SHGO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHGO_B200_VERSION 100
+
+#if defined(__GNUC__)
+#define SHGO_B200_API __attribute__((visibility("default")))
+#else
+#define SHGO_B200_API
+#endif
+
+enum {
+    SHGO_B200_OK = 0,
+    SHGO_B200_ERR_ARG = 1,      /* bad argument (null pointer, unsupported d, misalignment ...) */
+    SHGO_B200_ERR_CUDA = 2,     /* CUDA runtime error, incl. "no device" */
+    SHGO_B200_ERR_UNSUPPORTED = 3, /* functor / constraint-set combination not compiled in */
+    SHGO_B200_ERR_WORKSPACE = 4 /* caller workspace too small; required size reported */
+};
+
+/* Registered device functors (objective).  The numpy definition of each one, i.e. the Python
+ * callable a reference user passes as `func`, lives in shgo_b200/functors.py. */
+enum {
+    SHGO_B200_F_ROSENBROCK = 0,      /* scipy.optimize.rosen, any d >= 2 */
+    SHGO_B200_F_RASTRIGIN = 1,       /* 10 d + sum(x^2 - 10 cos(2 pi x)) */
+    SHGO_B200_F_ACKLEY = 2,
+    SHGO_B200_F_STYBLINSKI_TANG = 3, /* 0.5 sum(x^4 - 16 x^2 + 5 x) */
+    SHGO_B200_F_EGGHOLDER = 4,       /* d == 2, reference _shgo.py:329-333 */
+    SHGO_B200_F_CATTLE_FEED = 5,     /* d == 4, reference _shgo.py:408-409 */
+    SHGO_B200_F_SPHERE = 6           /* x0^2 + x1^2 + ... left to right */
+};
+/* Registered constraint sets g_i(x) >= 0 (reference: `ineq` constraints only, _shgo.py:544-556) */
+enum {
+    SHGO_B200_G_NONE = 0,
+    SHGO_B200_G_CATTLE_FEED = 1, /* g1, g2 of reference _shgo.py:411-418, d == 4 */
+    SHGO_B200_G_SUM_LE_6 = 2     /* -(sum(x) - 6) >= 0, reference tests/test__shgo.py:44-45 */
+};
+
+SHGO_B200_API int shgo_b200_version(void);
+SHGO_B200_API const char *shgo_b200_last_error(void);
+/* sm count, compute capability and memory of `device`; fails loudly when there is no GPU */
+SHGO_B200_API int shgo_b200_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
+                          size_t *total_mem);
+
+/* ---- a1 + a2: Sobol points --------------------------------------------------------------
+ * Replaces qmc.Sobol(d, scramble=False, seed=0).random(n) followed by the bounds scaling
+ * loop (reference _shgo.py:703-711, 1441-1449).  Writes points k0 .. k0+n-1 of the
+ * unscrambled 30-bit sequence, x = fl(fl(u * (ub - lb)) + lb), bit-identical to the reference.
+ *   sv      [d][30] uint32 direction numbers (scipy's `_sv`; see shgo_b200/_sobol.py)
+ *   lb, ub  [d] double
+ *   x       layout 0: SoA [d][ld] (coordinate-major, ld >= n); layout 1: AoS [n][d] (the
+ *           reference's C-order `self.C`)
+ */
+SHGO_B200_API int shgo_b200_sobol_fill(const uint32_t *sv, int d, uint64_t k0, uint64_t n, const double *lb,
+                         const double *ub, double *x, uint64_t ld, int layout, void *stream);
+
+/* ---- a1..a4 fused: generate -> scale -> evaluate f, g -> mask ---------------------------------
+ * Replaces, for a registered functor, VertexCacheField.process_pools' evaluation half
+ * (reference _vertex.py:324-385: feasibility_check + compute_sfield) on points that are never
+ * materialised.  f[i] = +inf when some g_j(x_i) < 0 or when the objective is NaN
+ * (_vertex.py:330-336, 351-352).  feasible may be NULL.
+ */
+SHGO_B200_API int shgo_b200_eval_sobol(int functor, int gset, int d, uint64_t k0, uint64_t n,
+                         const uint32_t *sv, const double *lb, const double *ub, double *f,
+                         uint8_t *feasible, void *stream);
+/* same evaluation on caller-supplied points, SoA [d][ld] */
+SHGO_B200_API int shgo_b200_eval_points(int functor, int gset, int d, uint64_t n, const double *x_soa,
+                          uint64_t ld, double *f, uint8_t *feasible, void *stream);
+/* arbitrary (torch-vectorised) callables: the caller produced f [n] and g [m][n] itself; this
+ * applies the reference's masking rules in place: feasible <=> no g_j < 0 (NaN g is feasible),
+ * infeasible or NaN f -> +inf.  g may be NULL (m = 0). */
+SHGO_B200_API int shgo_b200_mask_infeasible(double *f, uint64_t n, const double *g, int m, uint8_t *feasible,
+                              void *stream);
+
+/* ---- a5: vertex-face mesh -> vertex-vertex graph ------------------------------------------------
+ * Replaces Complex.vf_to_vv (reference _complex.py:1053-1074).  For dp1 >= 3 each simplex
+ * contributes the edges among its first three slots only; for dp1 == 2 the pair itself.  Output is
+ * a symmetric CSR with ascending, de-duplicated rows; vertices that never occupy a connecting
+ * slot get an empty row (they do not exist in the reference's vertex cache).
+ *   simplices [S][dp1] int32;  row_ptr [n+1] int64;  col [col_cap] int32 (6*S always suffices)
+ *   nnz       device uint64 receiving the number of directed entries
+ *   tmp       workspace; call shgo_b200_csr_workspace() for the size
+ */
+SHGO_B200_API size_t shgo_b200_csr_workspace(uint64_t S, int dp1, uint64_t n);
+SHGO_B200_API int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, uint64_t n,
+                                 int64_t *row_ptr, int32_t *col, uint64_t col_cap, uint64_t *nnz,
+                                 void *tmp, size_t tmp_bytes, void *stream);
+
+/* ---- a6: star test ------------------------------------------------------------------------------------
+ * Replaces VertexScalarField.minimiser / proc_minimisers (reference _vertex.py:144-151,
+ * 422-426): is_min[r] = 1 iff row row0+r is non-empty and f[row0+r] < f[w] (strict) for every
+ * neighbour w.  `row_ptr`/`col` address the whole graph, `f` the whole (gathered) vector; the
+ * call classifies rows [row0, row0+rows) -- the shard of one GPU.
+ */
+SHGO_B200_API int shgo_b200_star_csr(const int64_t *row_ptr, const int32_t *col, const double *f,
+                       uint64_t row0, uint64_t rows, uint8_t *is_min, void *stream);
+
+/* ---- a7: pool extraction ----------------------------------------------------------------------------
+ * Replaces the scan over HC.V.cache in SHGO.minimizers (reference _shgo.py:1109-1157):
+ * idx_out receives base + i for every i with is_min[i] != 0, ascending; *count the total.
+ * idx_out needs room for cap entries; entries beyond cap are counted but not written.
+ */
+SHGO_B200_API size_t shgo_b200_compact_workspace(uint64_t n);
+SHGO_B200_API int shgo_b200_compact_pool(const uint8_t *is_min, uint64_t n, int64_t base, int64_t *idx_out,
+                           uint64_t cap, uint64_t *count, void *tmp, size_t tmp_bytes,
+                           void *stream);
+
+/* ---- a11: find_lowest_vertex (reference _shgo.py:863-880) ---------------------------------------
+ * arg-min of f over vertices with present[i] != 0 (present may be NULL = all); ties resolve to the
+ * lowest index; *idx = -1 and *val = +inf when nothing is finite.  tmp: 16 * 1024 bytes. */
+SHGO_B200_API int shgo_b200_argmin(const double *f, const uint8_t *present, uint64_t n, int64_t *idx,
+                     double *val, void *tmp, size_t tmp_bytes, void *stream);
+
+/* nfev bookkeeping (reference _vertex.py:184,347): number of vertices that exist (non-empty
+ * row) and are feasible (feasible may be NULL). */
+SHGO_B200_API int shgo_b200_count_nfev(const int64_t *row_ptr, const uint8_t *feasible, uint64_t n,
+                         uint64_t *count, void *stream);
+
+/* ---- a8 + a9: whole-generation simplicial complex ---------------------------------------------
+ * Replaces Complex.triangulate / refine_all (reference _complex.py:192-472, 514-976) by the
+ * closed form of SURVEY.md Appendix B.  gen = completed refinements, K = 2^gen cells per axis.
+ * Vertex ids: grid vertex k in [0,K]^d -> sum k_i (K+1)^i ; centroid c in [0,K)^d ->
+ * (K+1)^d + sum c_i K^i.  tab [d][2^(gen+1)+1] holds the per-axis coordinates (built on the host
+ * by recursive midpointing, shgo_b200/lattice.py).
+ */
+SHGO_B200_API int shgo_b200_lattice_eval(int functor, int gset, int d, int gen, const double *tab,
+                           uint64_t v0, uint64_t nv, double *f, uint8_t *feasible, void *stream);
+/* coordinates of vertices v0 .. v0+nv-1, SoA [d][ld] */
+SHGO_B200_API int shgo_b200_lattice_coords(int d, int gen, const double *tab, uint64_t v0, uint64_t nv,
+                             double *x_soa, uint64_t ld, void *stream);
+/* implicit-adjacency star test over vertices v0 .. v0+nv-1; f is the whole vector */
+SHGO_B200_API int shgo_b200_lattice_star(int d, int gen, const double *f, uint64_t v0, uint64_t nv,
+                           uint8_t *is_min, void *stream);
+
+/* ---- host-buffer convenience path (what bench.py's `e2e` times) ---------------------------------
+ * One shgo iteration of the Sobol path with HOST inputs and outputs: uploads the CSR (pinned or
+ * pageable host memory), generates + evaluates + masks on the device, classifies, compacts and
+ * copies the pool indices back.  All device memory lives in the ctx and is reused across calls.
+ */
+typedef struct shgo_b200_ctx shgo_b200_ctx;
+SHGO_B200_API int shgo_b200_ctx_create(int device, shgo_b200_ctx **out);
+SHGO_B200_API void shgo_b200_ctx_destroy(shgo_b200_ctx *ctx);
+SHGO_B200_API int shgo_b200_iterate_sobol_host(shgo_b200_ctx *ctx, int functor, int gset, int d, uint64_t k0,
+                                 uint64_t n, const uint32_t *sv /*[host]*/,
+                                 const double *lb /*[host]*/, const double *ub /*[host]*/,
+                                 const int64_t *row_ptr /*[host] n+1*/,
+                                 const int32_t *col /*[host] nnz*/, int64_t *pool_idx /*[host]*/,
+                                 uint64_t pool_cap, uint64_t *pool_count /*[host]*/,
+                                 uint64_t *nfev /*[host]*/, double *f_out /*[host] n or NULL*/);
+
+/* ---- measurement helper ------------------------------------------------------------------------------
+ * Dependent-chain-free DFMA loop; *flops = FP64 flops performed.  Used by bench.py to measure the
+ * FP64 pipe peak on the box (no published number is trusted). */
+SHGO_B200_API int shgo_b200_fp64_peak(int iters, double *sink, uint64_t *flops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHGO_B200_H */

@@ -1,0 +1,539 @@
+// graph.cu -- K3 (vertex-face mesh -> CSR), K4 (CSR star test), pool compaction, arg-min and
+// nfev bookkeeping.  Integer / byte work bound by HBM; no tensor cores involved.
+#include "common.cuh"
+
+namespace shgo_b200 {
+
+// =============================================================================================
+// K4: star test over an explicit CSR  (reference _vertex.py:144-151, 422-426)
+//
+// A CTA owns a tile of 256 consecutive rows.  The tile's slice of `col` is one contiguous range
+// col[row_ptr[r0] .. row_ptr[r0+256]) and is staged into shared memory with coalesced 16-byte
+// loads, so `col` (4*nnz bytes, the bulk of the compulsory traffic) streams from HBM exactly once
+// at full sector efficiency.  Then one thread walks one row: neighbour ids come from shared
+// memory, neighbour f values are gathered through L1/L2 with ld.global.nc, four at a time, and a
+// row stops as soon as one neighbour is not strictly larger (the reference's all() also
+// short-circuits) -- on average only ~H(deg) gathers per row are issued.  Mapping thread <-> row
+// (not warp <-> row) makes the gathers of a warp hit neighbouring sectors whenever consecutive
+// rows have "parallel" neighbour lists, which is the case for lattice-like graphs.
+// Rows whose tile slice exceeds the staging buffer fall back to reading `col` from global memory.
+// =============================================================================================
+constexpr int kStarThreads = 256;
+constexpr int kStarCap = 12288;  // int32 entries staged per tile (48 KB)
+
+__global__ void __launch_bounds__(kStarThreads)
+star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                const double *__restrict__ f, uint64_t row0, uint64_t rows,
+                uint8_t *__restrict__ is_min)
+{
+    __shared__ __align__(16) int32_t scol[kStarCap];
+    const uint64_t ntiles = (rows + kStarThreads - 1) / kStarThreads;
+    const int t = threadIdx.x;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t lr0 = tile * kStarThreads;
+        const uint64_t nrow = rows - lr0 < (uint64_t)kStarThreads ? rows - lr0 : kStarThreads;
+        const bool valid = (uint64_t)t < nrow;
+        const uint64_t r = row0 + lr0 + (valid ? t : 0);
+        const int64_t b = row_ptr[r], e = row_ptr[r + 1];
+        const double fv = ld_nc_f64(f + r);
+        const int64_t s0 = row_ptr[row0 + lr0], s1 = row_ptr[row0 + lr0 + nrow];
+        const int64_t s0a = s0 & ~(int64_t)3;
+        const bool staged = (s1 - s0a) <= kStarCap;
+        if (staged) {
+            const int64_t nvec = (s1 - s0a) >> 2;  // full 16-byte vectors inside the slice
+            const int4 *src = reinterpret_cast<const int4 *>(col + s0a);
+            int4 *dst = reinterpret_cast<int4 *>(scol);
+            for (int64_t v = t; v < nvec; v += kStarThreads) dst[v] = __ldg(src + v);
+            for (int64_t k = s0a + (nvec << 2) + t; k < s1; k += kStarThreads)
+                scol[k - s0a] = __ldg(col + k);
+        }
+        __syncthreads();
+        bool ok = valid && e > b;
+        if (staged) {
+            for (int64_t k = b; k < e && ok; k += 4) {
+                int32_t nb[4];
+                double fn[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) nb[u] = k + u < e ? scol[k + u - s0a] : -1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) fn[u] = nb[u] >= 0 ? ld_nc_f64(f + nb[u]) : pos_inf();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ok = ok && (fv < fn[u]);
+            }
+        } else {
+            for (int64_t k = b; k < e && ok; ++k) ok = fv < ld_nc_f64(f + __ldg(col + k));
+        }
+        if (valid) is_min[lr0 + t] = ok ? 1 : 0;
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
+// Multi-block exclusive scan of small counts (uint8 flags or uint32 degrees) into 64-bit offsets.
+//   pass 1: per-block sums (4096 items per block)   pass 2: one CTA scans the block sums
+//   pass 3: callers re-scan inside each block and add the block offset
+// =============================================================================================
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanBlock = kScanThreads * kScanItems;  // 4096
+
+template <class T>
+__device__ __forceinline__ uint32_t load_items(const T *in, uint64_t base, uint64_t n,
+                                               uint32_t (&v)[kScanItems])
+{
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        uint64_t k = base + i;
+        v[i] = k < n ? (uint32_t)(in[k] != 0 ? (sizeof(T) == 1 ? 1u : (uint32_t)in[k]) : 0u) : 0u;
+        s += v[i];
+    }
+    return s;
+}
+
+// exclusive scan of one value per thread across the CTA; returns the exclusive prefix, *total
+// the CTA sum
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t *total)
+{
+    __shared__ uint32_t warp_sums[kScanThreads / 32];
+    __shared__ uint32_t block_total;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t ws = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+        uint32_t winc = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += y;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = winc - ws;
+        if (lane == 31) block_total = winc;
+    }
+    __syncthreads();
+    uint32_t res = warp_sums[w] + inc - x;
+    *total = block_total;
+    __syncthreads();
+    return res;
+}
+
+template <class T>
+__global__ void __launch_bounds__(kScanThreads)
+block_sum_kernel(const T *__restrict__ in, uint64_t n, uint64_t *__restrict__ sums)
+{
+    uint32_t v[kScanItems];
+    uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t s = load_items(in, base, n, v);
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// one CTA: in-place exclusive scan of nb 64-bit block sums; grand total -> *total
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint64_t *sums, uint64_t nb, uint64_t *total)
+{
+    __shared__ uint64_t wsum[32];
+    __shared__ uint64_t chunk_total;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t carry = 0;  // identical in every thread
+    for (uint64_t base = 0; base < nb; base += 1024) {
+        const uint64_t k = base + threadIdx.x;
+        const uint64_t x = k < nb ? sums[k] : 0;
+        uint64_t inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            const uint64_t ws = wsum[lane];
+            uint64_t winc = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint64_t y = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += y;
+            }
+            wsum[lane] = winc - ws;
+            if (lane == 31) chunk_total = winc;
+        }
+        __syncthreads();
+        if (k < nb) sums[k] = carry + wsum[w] + inc - x;
+        carry += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// pool compaction, pass 3: ascending indices of the non-zero flags
+__global__ void __launch_bounds__(kScanThreads)
+compact_scatter_kernel(const uint8_t *__restrict__ flags, uint64_t n, const uint64_t *__restrict__ offs,
+                       int64_t base_index, int64_t *__restrict__ idx_out, uint64_t cap)
+{
+    uint32_t v[kScanItems];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t s = load_items(flags, base, n, v);
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, &total);
+    if (s == 0) return;
+    uint64_t o = offs[blockIdx.x] + ex;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+        if (v[i]) {
+            if (o < cap) idx_out[o] = base_index + (int64_t)(base + i);
+            ++o;
+        }
+}
+
+// CSR build, pass 3: row_ptr[i] = exclusive prefix of deg; row_ptr[n] = nnz
+__global__ void __launch_bounds__(kScanThreads)
+rowptr_kernel(const uint32_t *__restrict__ deg, uint64_t n, const uint64_t *__restrict__ offs,
+              int64_t *__restrict__ row_ptr)
+{
+    uint32_t v[kScanItems];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
+    uint32_t s = load_items(deg, base, n, v);
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, &total);
+    uint64_t o = offs[blockIdx.x] + ex;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (base + i <= n) row_ptr[base + i] = (int64_t)o;  // base+i == n writes nnz
+        o += v[i];
+    }
+}
+
+// =============================================================================================
+// K3: vf_to_vv (reference _complex.py:1053-1074).  Undirected edges among simplex slots 0,1,2
+// (dp1 >= 3) or the pair itself (dp1 == 2) are de-duplicated in an open-addressing hash set
+// (64-bit keys min<<32|max, linear probing, atomicCAS), degrees are counted on first insertion,
+// rows are filled by atomic cursors and finally rank-sorted, one warp per row, so that the CSR
+// is deterministic.
+// =============================================================================================
+constexpr uint64_t kEmptyKey = ~0ull;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+__global__ void edge_insert_kernel(const int32_t *__restrict__ simplices, uint64_t S, int dp1,
+                                   uint64_t n, unsigned long long *__restrict__ table,
+                                   uint64_t mask, uint32_t *__restrict__ deg, int *__restrict__ bad)
+{
+    const int npair = dp1 >= 3 ? 3 : 1;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < S;
+         s += (uint64_t)gridDim.x * blockDim.x) {
+        const int32_t *sp = simplices + s * (uint64_t)dp1;
+        int32_t v[3];
+        v[0] = __ldg(sp);
+        v[1] = __ldg(sp + 1);
+        v[2] = dp1 >= 3 ? __ldg(sp + 2) : 0;
+        for (int e = 0; e < npair; ++e) {
+            int32_t a = v[e == 2 ? 1 : 0], b = v[e == 0 ? 1 : 2];
+            if (a == b) continue;  // connect(): `v is not self` (_vertex.py:123)
+            if ((uint32_t)a >= n || (uint32_t)b >= n) {
+                *bad = 1;
+                continue;
+            }
+            uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+            unsigned long long key = ((unsigned long long)lo << 32) | hi;
+            uint64_t h = mix64(key) & mask;
+            while (true) {
+                unsigned long long prev = atomicCAS(table + h, kEmptyKey, key);
+                if (prev == kEmptyKey) {
+                    atomicAdd(deg + lo, 1u);
+                    atomicAdd(deg + hi, 1u);
+                    break;
+                }
+                if (prev == key) break;
+                h = (h + 1) & mask;
+            }
+        }
+    }
+}
+
+__global__ void edge_fill_kernel(const unsigned long long *__restrict__ table, uint64_t slots,
+                                 const int64_t *__restrict__ row_ptr, uint32_t *__restrict__ cursor,
+                                 int32_t *__restrict__ col_tmp)
+{
+    for (uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; h < slots;
+         h += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long key = table[h];
+        if (key == kEmptyKey) continue;
+        uint32_t lo = (uint32_t)(key >> 32), hi = (uint32_t)key;
+        col_tmp[row_ptr[lo] + atomicAdd(cursor + lo, 1u)] = (int32_t)hi;
+        col_tmp[row_ptr[hi] + atomicAdd(cursor + hi, 1u)] = (int32_t)lo;
+    }
+}
+
+// one warp per row: rank sort (entries of a row are distinct), col_tmp -> col
+__global__ void __launch_bounds__(256)
+row_sort_kernel(const int64_t *__restrict__ row_ptr, uint64_t n, const int32_t *__restrict__ col_tmp,
+                int32_t *__restrict__ col)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        const int64_t b = row_ptr[r], e = row_ptr[r + 1];
+        for (int64_t i = b + lane; i < e; i += 32) {
+            const int32_t v = col_tmp[i];
+            int64_t rank = 0;
+            for (int64_t k = b; k < e; ++k) rank += col_tmp[k] < v;
+            col[b + rank] = v;
+        }
+    }
+}
+
+// =============================================================================================
+// arg-min (find_lowest_vertex, reference _shgo.py:863-880) and nfev (reference _vertex.py:184,347)
+// =============================================================================================
+struct MinPair {
+    double v;
+    int64_t i;
+};
+__device__ __forceinline__ MinPair min_pair(MinPair a, MinPair b)
+{
+    if (b.i >= 0 && (a.i < 0 || b.v < a.v || (b.v == a.v && b.i < a.i))) return b;
+    return a;
+}
+__device__ __forceinline__ MinPair block_min(MinPair m)
+{
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MinPair y{__shfl_down_sync(0xffffffffu, m.v, o), __shfl_down_sync(0xffffffffu, m.i, o)};
+        m = min_pair(m, y);
+    }
+    if (lane == 0) {
+        sv[w] = m.v;
+        si[w] = m.i;
+    }
+    __syncthreads();
+    if (w == 0) {
+        m = lane < nw ? MinPair{sv[lane], si[lane]} : MinPair{pos_inf(), -1};
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            MinPair y{__shfl_down_sync(0xffffffffu, m.v, o), __shfl_down_sync(0xffffffffu, m.i, o)};
+            m = min_pair(m, y);
+        }
+    }
+    return m;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256)
+argmin_partial_kernel(const double *__restrict__ f, const uint8_t *__restrict__ present, uint64_t n,
+                      MinPair *__restrict__ partial)
+{
+    MinPair m{pos_inf(), -1};
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        if (present && !present[i]) continue;
+        double v = ld_nc_f64(f + i);
+        if (v < m.v) {  // strict: +inf never wins, first (lowest) index wins ties
+            m.v = v;
+            m.i = (int64_t)i;
+        }
+    }
+    m = block_min(m);
+    if (threadIdx.x == 0) partial[blockIdx.x] = m;
+}
+
+__global__ void __launch_bounds__(1024)
+argmin_final_kernel(const MinPair *__restrict__ partial, int nparts, int64_t *idx, double *val)
+{
+    MinPair m{pos_inf(), -1};
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) m = min_pair(m, partial[i]);
+    m = block_min(m);
+    if (threadIdx.x == 0) {
+        *idx = m.i;
+        *val = m.i >= 0 ? m.v : pos_inf();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+nfev_kernel(const int64_t *__restrict__ row_ptr, const uint8_t *__restrict__ feasible, uint64_t n,
+            unsigned long long *__restrict__ count)
+{
+    unsigned long long c = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        c += (row_ptr[i + 1] > row_ptr[i]) && (!feasible || feasible[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+static inline uint64_t next_pow2(uint64_t x)
+{
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline unsigned grid_for(uint64_t items, int threads, int per_sm)
+{
+    uint64_t b = (items + threads - 1) / threads;
+    uint64_t cap = (uint64_t)sm_count() * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace shgo_b200
+
+using namespace shgo_b200;
+
+extern "C" {
+
+int shgo_b200_star_csr(const int64_t *row_ptr, const int32_t *col, const double *f, uint64_t row0,
+                       uint64_t rows, uint8_t *is_min, void *stream)
+{
+    SHGO_REQUIRE(row_ptr && f && is_min, "null pointer");
+    SHGO_REQUIRE(col || rows == 0, "null col");
+    SHGO_REQUIRE((reinterpret_cast<uintptr_t>(col) & 15) == 0, "col must be 16-byte aligned");
+    if (rows == 0) return SHGO_B200_OK;
+    int occ = 0;
+    SHGO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, star_csr_kernel, kStarThreads, 0));
+    if (occ < 1) occ = 1;
+    uint64_t tiles = (rows + kStarThreads - 1) / kStarThreads;
+    uint64_t grid = (uint64_t)sm_count() * occ;
+    if (grid > tiles) grid = tiles;
+    star_csr_kernel<<<(unsigned)grid, kStarThreads, 0, as_stream(stream)>>>(row_ptr, col, f, row0, rows,
+                                                                          is_min);
+    SHGO_CUDA_TRY(cudaGetLastError());
+    return SHGO_B200_OK;
+}
+
+size_t shgo_b200_compact_workspace(uint64_t n)
+{
+    uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
+    return align256((nb + 2) * sizeof(uint64_t));
+}
+
+int shgo_b200_compact_pool(const uint8_t *is_min, uint64_t n, int64_t base, int64_t *idx_out,
+                           uint64_t cap, uint64_t *count, void *tmp, size_t tmp_bytes, void *stream)
+{
+    SHGO_REQUIRE(count && tmp, "null pointer");
+    SHGO_REQUIRE(is_min || n == 0, "null flags");
+    SHGO_REQUIRE(idx_out || cap == 0, "null idx_out with cap > 0");
+    if (tmp_bytes < shgo_b200_compact_workspace(n))
+        return fail(SHGO_B200_ERR_WORKSPACE, "compact workspace: need %zu bytes, got %zu",
+                    shgo_b200_compact_workspace(n), tmp_bytes);
+    cudaStream_t st = as_stream(stream);
+    if (n == 0) {
+        SHGO_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint64_t), st));
+        return SHGO_B200_OK;
+    }
+    uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
+    uint64_t *sums = static_cast<uint64_t *>(tmp);
+    block_sum_kernel<uint8_t><<<(unsigned)nb, kScanThreads, 0, st>>>(is_min, n, sums);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, count);
+    compact_scatter_kernel<<<(unsigned)nb, kScanThreads, 0, st>>>(is_min, n, sums, base, idx_out, cap);
+    SHGO_CUDA_TRY(cudaGetLastError());
+    return SHGO_B200_OK;
+}
+
+size_t shgo_b200_csr_workspace(uint64_t S, int dp1, uint64_t n)
+{
+    uint64_t pairs = dp1 >= 3 ? 3 * S : S;
+    uint64_t slots = next_pow2(pairs * 2 < 64 ? 64 : pairs * 2);
+    uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
+    return align256(slots * 8) + 2 * align256(n * 4) + align256(pairs * 2 * 4 + 16) +
+           align256((nb + 2) * 8) + align256(16);
+}
+
+int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, uint64_t n,
+                                 int64_t *row_ptr, int32_t *col, uint64_t col_cap, uint64_t *nnz,
+                                 void *tmp, size_t tmp_bytes, void *stream)
+{
+    SHGO_REQUIRE(row_ptr && nnz && tmp, "null pointer");
+    SHGO_REQUIRE(simplices || S == 0, "null simplices");
+    SHGO_REQUIRE(dp1 >= 2, "simplices need at least two vertex slots (dp1 = %d)", dp1);
+    SHGO_REQUIRE(n >= 1 && n <= 0x7fffffffull, "vertex count out of int32 range");
+    const uint64_t pairs = dp1 >= 3 ? 3 * S : S;
+    SHGO_REQUIRE(col_cap >= 2 * pairs, "col capacity %llu < %llu", (unsigned long long)col_cap,
+                 (unsigned long long)(2 * pairs));
+    SHGO_REQUIRE(col || pairs == 0, "null col");
+    if (tmp_bytes < shgo_b200_csr_workspace(S, dp1, n))
+        return fail(SHGO_B200_ERR_WORKSPACE, "csr workspace: need %zu bytes, got %zu",
+                    shgo_b200_csr_workspace(S, dp1, n), tmp_bytes);
+    cudaStream_t st = as_stream(stream);
+    const uint64_t slots = next_pow2(pairs * 2 < 64 ? 64 : pairs * 2);
+    const uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
+    unsigned char *p = static_cast<unsigned char *>(tmp);
+    unsigned long long *table = reinterpret_cast<unsigned long long *>(p);
+    p += align256(slots * 8);
+    uint32_t *deg = reinterpret_cast<uint32_t *>(p);
+    p += align256(n * 4);
+    uint32_t *cursor = reinterpret_cast<uint32_t *>(p);
+    p += align256(n * 4);
+    int32_t *col_tmp = reinterpret_cast<int32_t *>(p);
+    p += align256(pairs * 2 * 4 + 16);
+    uint64_t *sums = reinterpret_cast<uint64_t *>(p);
+    p += align256((nb + 2) * 8);
+    int *bad = reinterpret_cast<int *>(p);
+
+    SHGO_CUDA_TRY(cudaMemsetAsync(table, 0xff, slots * 8, st));
+    SHGO_CUDA_TRY(cudaMemsetAsync(deg, 0, align256(n * 4) * 2, st));  // deg + cursor
+    SHGO_CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    if (S > 0)
+        edge_insert_kernel<<<grid_for(S, 256, 8), 256, 0, st>>>(simplices, S, dp1, n, table, slots - 1,
+                                                                deg, bad);
+    block_sum_kernel<uint32_t><<<(unsigned)nb, kScanThreads, 0, st>>>(deg, n, sums);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, nnz);
+    rowptr_kernel<<<(unsigned)nb, kScanThreads, 0, st>>>(deg, n, sums, row_ptr);
+    if (S > 0) {
+        edge_fill_kernel<<<grid_for(slots, 256, 8), 256, 0, st>>>(table, slots, row_ptr, cursor, col_tmp);
+        row_sort_kernel<<<grid_for(n * 32, 256, 8), 256, 0, st>>>(row_ptr, n, col_tmp, col);
+    }
+    SHGO_CUDA_TRY(cudaGetLastError());
+    return SHGO_B200_OK;
+}
+
+int shgo_b200_argmin(const double *f, const uint8_t *present, uint64_t n, int64_t *idx, double *val,
+                     void *tmp, size_t tmp_bytes, void *stream)
+{
+    SHGO_REQUIRE(idx && val && tmp, "null pointer");
+    SHGO_REQUIRE(f || n == 0, "null f");
+    SHGO_REQUIRE(tmp_bytes >= 1024 * sizeof(MinPair), "argmin workspace: need %zu bytes",
+                 1024 * sizeof(MinPair));
+    cudaStream_t st = as_stream(stream);
+    unsigned blocks = grid_for(n ? n : 1, 256, 4);
+    if (blocks > 1024) blocks = 1024;
+    MinPair *partial = static_cast<MinPair *>(tmp);
+    argmin_partial_kernel<<<blocks, 256, 0, st>>>(f, present, n, partial);
+    argmin_final_kernel<<<1, 1024, 0, st>>>(partial, (int)blocks, idx, val);
+    SHGO_CUDA_TRY(cudaGetLastError());
+    return SHGO_B200_OK;
+}
+
+int shgo_b200_count_nfev(const int64_t *row_ptr, const uint8_t *feasible, uint64_t n, uint64_t *count,
+                         void *stream)
+{
+    SHGO_REQUIRE(row_ptr && count, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    SHGO_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint64_t), st));
+    if (n == 0) return SHGO_B200_OK;
+    nfev_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(row_ptr, feasible, n,
+                                                    reinterpret_cast<unsigned long long *>(count));
+    SHGO_CUDA_TRY(cudaGetLastError());
+    return SHGO_B200_OK;
+}
+
+}  // extern "C"

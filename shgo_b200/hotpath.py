@@ -1,0 +1,232 @@
+"""Tensor-level front end of the C ABI: the hot path on torch CUDA tensors.
+
+PyTorch is plumbing here (device memory, streams); every function below is one or two calls into
+libshgo_b200.so on ``torch.cuda.current_stream()``.  Nothing falls back to the CPU.
+
+Reference functions replaced (paths relative to the reference checkout):
+  sobol_points / eval_sobol   qmc.Sobol.random + bounds scaling + compute_sfield/feasibility_check
+                              (shgo/_shgo.py:703-711,1441-1449; shgo/_shgo_lib/_vertex.py:330-352)
+  csr_from_simplices          Complex.vf_to_vv (shgo/_shgo_lib/_complex.py:1053-1074)
+  star_csr / lattice_star     VertexScalarField.minimiser (shgo/_shgo_lib/_vertex.py:144-151)
+  compact_pool / argmin       SHGO.minimizers / find_lowest_vertex (shgo/_shgo.py:1109-1157,863-880)
+"""
+import numpy as np
+import torch
+
+from . import _lib, _sobol
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("shgo_b200 needs a CUDA device (B200); there is no CPU fallback")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _dev(device=None):
+    _require_cuda()
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+class SobolTables:
+    """Device copies of the direction numbers and bounds of one problem."""
+
+    def __init__(self, bounds, device=None):
+        device = _dev(device)
+        b = np.asarray(bounds, np.float64)
+        self.d = b.shape[0]
+        self.lb_host, self.ub_host = b[:, 0].copy(), b[:, 1].copy()
+        self.sv_host = np.ascontiguousarray(_sobol.direction_numbers(self.d))
+        # kernels read the tables as uint32; torch has no unsigned 32-bit arithmetic, so ship bits
+        self.sv = torch.from_numpy(self.sv_host.view(np.int32).copy()).to(device)
+        self.lb = torch.from_numpy(self.lb_host).to(device)
+        self.ub = torch.from_numpy(self.ub_host).to(device)
+        span = self.ub_host - self.lb_host
+        scaled = span * 2.0 ** -30
+        if not (np.all(np.isfinite(span)) and np.all(scaled * 2.0 ** 30 == span)
+                and np.all((scaled == 0) | (np.abs(scaled) > 1e-290))):
+            raise ValueError("bounds span not exactly scalable by 2^-30; unsupported")
+
+
+def sobol_points(tab, k0, n, layout="soa", out=None):
+    """Points k0..k0+n-1 scaled to the bounds, bit-identical to the reference's `self.C`.
+
+    layout 'soa' -> (d, n) coordinate-major; 'aos' -> (n, d) like the reference."""
+    d = tab.d
+    dev = tab.sv.device
+    if layout == "soa":
+        x = out if out is not None else torch.empty((d, n), dtype=torch.float64, device=dev)
+        _lib.call("shgo_b200_sobol_fill", _ptr(tab.sv), d, k0, n, _ptr(tab.lb), _ptr(tab.ub), _ptr(x),
+                  x.stride(0) if n else max(n, 1), 0, _stream())
+    else:
+        x = out if out is not None else torch.empty((n, d), dtype=torch.float64, device=dev)
+        _lib.call("shgo_b200_sobol_fill", _ptr(tab.sv), d, k0, n, _ptr(tab.lb), _ptr(tab.ub), _ptr(x),
+                  0, 1, _stream())
+    return x
+
+
+def eval_sobol(functor, gset, tab, k0, n, f=None, feasible=None, want_feasible=True):
+    """Fused generate -> scale -> evaluate -> mask over Sobol indices [k0, k0+n)."""
+    dev = tab.sv.device
+    if f is None:
+        f = torch.empty(n, dtype=torch.float64, device=dev)
+    if feasible is None and want_feasible:
+        feasible = torch.empty(n, dtype=torch.uint8, device=dev)
+    _lib.call("shgo_b200_eval_sobol", functor, gset, tab.d, k0, n, _ptr(tab.sv), _ptr(tab.lb),
+              _ptr(tab.ub), _ptr(f), _ptr(feasible), _stream())
+    return f, feasible
+
+
+def eval_points(functor, gset, x_soa, f=None, feasible=None):
+    """Evaluate a registered functor on caller-supplied points, x_soa = (d, n) float64."""
+    assert x_soa.dtype == torch.float64 and x_soa.dim() == 2 and x_soa.stride(1) == 1
+    d, n = x_soa.shape
+    if f is None:
+        f = torch.empty(n, dtype=torch.float64, device=x_soa.device)
+    if feasible is None:
+        feasible = torch.empty(n, dtype=torch.uint8, device=x_soa.device)
+    _lib.call("shgo_b200_eval_points", functor, gset, d, n, _ptr(x_soa), x_soa.stride(0) if n else 1,
+              _ptr(f), _ptr(feasible), _stream())
+    return f, feasible
+
+
+def mask_infeasible(f, g=None, feasible=None):
+    """In place: f=+inf where any g<0 or f is NaN.  g = (m, n) float64 or None."""
+    n = f.numel()
+    m = 0 if g is None else g.shape[0]
+    if g is not None:
+        g = g.contiguous()
+    if feasible is None:
+        feasible = torch.empty(n, dtype=torch.uint8, device=f.device)
+    _lib.call("shgo_b200_mask_infeasible", _ptr(f), n, _ptr(g), m, _ptr(feasible), _stream())
+    return f, feasible
+
+
+def csr_from_simplices(simplices, n):
+    """Symmetric CSR (row_ptr int64 [n+1], col int32 [nnz]) of the reference's vertex graph."""
+    assert simplices.dtype == torch.int32 and simplices.dim() == 2
+    simplices = simplices.contiguous()
+    S, dp1 = simplices.shape
+    dev = simplices.device
+    pairs = 3 * S if dp1 >= 3 else S
+    row_ptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(max(2 * pairs, 4), dtype=torch.int32, device=dev)
+    nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _lib.lib().shgo_b200_csr_workspace(S, dp1, n)
+    tmp = torch.empty(ws, dtype=torch.uint8, device=dev)
+    _lib.call("shgo_b200_csr_from_simplices", _ptr(simplices), S, dp1, n, _ptr(row_ptr), _ptr(col),
+              col.numel(), _ptr(nnz), _ptr(tmp), ws, _stream())
+    return row_ptr, col[: int(nnz.item())]
+
+
+def star_csr(row_ptr, col, f, row0=0, rows=None, is_min=None):
+    n = row_ptr.numel() - 1
+    rows = n - row0 if rows is None else rows
+    if is_min is None:
+        is_min = torch.empty(rows, dtype=torch.uint8, device=f.device)
+    _lib.call("shgo_b200_star_csr", _ptr(row_ptr), _ptr(col), _ptr(f), row0, rows, _ptr(is_min), _stream())
+    return is_min
+
+
+class PoolWorkspace:
+    """Reusable buffers for compact_pool / argmin / nfev (no allocation inside timed regions)."""
+
+    def __init__(self, n, cap, device):
+        self.cap = cap
+        self.idx = torch.empty(max(cap, 1), dtype=torch.int64, device=device)
+        self.count = torch.zeros(2, dtype=torch.int64, device=device)
+        self.ws = _lib.lib().shgo_b200_compact_workspace(n)
+        self.tmp = torch.empty(max(self.ws, 16 * 1024), dtype=torch.uint8, device=device)
+
+
+def compact_pool(is_min, base=0, cap=None, work=None):
+    """Ascending indices (base + i) of the set flags.  Returns (idx tensor view, count tensor)."""
+    n = is_min.numel()
+    if work is None:
+        work = PoolWorkspace(n, n if cap is None else cap, is_min.device)
+    _lib.call("shgo_b200_compact_pool", _ptr(is_min), n, base, _ptr(work.idx), work.cap,
+              _ptr(work.count), _ptr(work.tmp), work.tmp.numel(), _stream())
+    return work.idx, work.count[0]
+
+
+def argmin(f, present=None):
+    dev = f.device
+    idx = torch.empty(1, dtype=torch.int64, device=dev)
+    val = torch.empty(1, dtype=torch.float64, device=dev)
+    tmp = torch.empty(16 * 1024, dtype=torch.uint8, device=dev)
+    _lib.call("shgo_b200_argmin", _ptr(f), _ptr(present), f.numel(), _ptr(idx), _ptr(val), _ptr(tmp),
+              tmp.numel(), _stream())
+    return int(idx.item()), float(val.item())
+
+
+def count_nfev(row_ptr, feasible=None, out=None):
+    if out is None:
+        out = torch.zeros(1, dtype=torch.int64, device=row_ptr.device)
+    _lib.call("shgo_b200_count_nfev", _ptr(row_ptr), _ptr(feasible), row_ptr.numel() - 1, _ptr(out), _stream())
+    return out
+
+
+def hypercube_csr(n, device=None):
+    """Synthetic CSR of BASELINE.md section 5 (NOT a Delaunay graph): vertex i ~ i XOR 2^j,
+    j < log2 n; int64 row_ptr / int32 col exactly as a qhull-derived CSR would be stored."""
+    device = _dev(device)
+    m = int(n).bit_length() - 1
+    assert 1 << m == n, "n must be a power of two"
+    row_ptr = torch.arange(0, (n + 1) * m, m, dtype=torch.int64, device=device)
+    bits = (1 << torch.arange(m, dtype=torch.int32, device=device))[None, :]
+    col = torch.empty((n, m), dtype=torch.int32, device=device)
+    step = 1 << 24
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        i = torch.arange(s, e, dtype=torch.int32, device=device)[:, None]
+        torch.bitwise_xor(i, bits, out=col[s:e])
+    return row_ptr, col.reshape(-1)
+
+
+# ---- whole-generation simplicial lattice ------------------------------------------------------
+def lattice_eval(functor, gset, d, gen, tab, v0, nv, f=None, feasible=None):
+    dev = tab.device
+    if f is None:
+        f = torch.empty(nv, dtype=torch.float64, device=dev)
+    if feasible is None:
+        feasible = torch.empty(nv, dtype=torch.uint8, device=dev)
+    _lib.call("shgo_b200_lattice_eval", functor, gset, d, gen, _ptr(tab), v0, nv, _ptr(f),
+              _ptr(feasible), _stream())
+    return f, feasible
+
+
+def lattice_coords(d, gen, tab, v0, nv):
+    x = torch.empty((d, nv), dtype=torch.float64, device=tab.device)
+    _lib.call("shgo_b200_lattice_coords", d, gen, _ptr(tab), v0, nv, _ptr(x), max(nv, 1), _stream())
+    return x
+
+
+def lattice_star(d, gen, f, v0=0, nv=None, is_min=None):
+    nv = f.numel() - v0 if nv is None else nv
+    if is_min is None:
+        is_min = torch.empty(nv, dtype=torch.uint8, device=f.device)
+    _lib.call("shgo_b200_lattice_star", d, gen, _ptr(f), v0, nv, _ptr(is_min), _stream())
+    return is_min
+
+
+def fp64_peak_tflops(iters=4096, repeats=5):
+    """Measured FP64 DFMA throughput of the current device (TFLOP/s)."""
+    _require_cuda()
+    import ctypes
+    sink = torch.zeros(1, dtype=torch.float64, device="cuda")
+    flops = ctypes.c_uint64(0)
+    best = 0.0
+    for _ in range(repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("shgo_b200_fp64_peak", iters, _ptr(sink), ctypes.byref(flops), _stream())
+        e1.record()
+        e1.synchronize()
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

@@ -1,0 +1,375 @@
+"""Parity of the CUDA hot path against the CPU oracle and the golden fixtures (B200 only).
+
+Every call goes through the C ABI (shgo_b200.hotpath is a ctypes shim over libshgo_b200.so).
+Bars: Sobol points, adjacency, feasibility and pool index sets bit-exact; f bit-exact for the
+polynomial / FMA-chain functors and within 1e-12 (relative to max(|f|, 1)) for the ones that go
+through cos/sin/exp.
+"""
+import numpy as np
+import pytest
+
+from conftest import (BIT_EXACT_F, LATTICE_CASES, SIMPLICIAL_POOL_CASES, SOBOL_CASES, gset_of,
+                      load_golden)
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as orc  # noqa: E402
+
+DEVICE_BIT_EXACT = BIT_EXACT_F | {"styblinski_tang"}   # device == C oracle bit for bit
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def hp():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from shgo_b200 import hotpath
+    return hotpath
+
+
+def _ids(functor, gset):
+    return orc.FUNCTOR_IDS[functor], orc.GSET_IDS[gset]
+
+
+def _close(a, b):
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isinf(a), np.isinf(b))
+    if fin.any():
+        scale = np.maximum(np.abs(b[fin]), 1.0)
+        assert np.max(np.abs(a[fin] - b[fin]) / scale) < RTOL
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,k0,n", [(1, 0, 1), (2, 0, 1000), (6, 0, 4096), (8, 12345, 70001),
+                                    (10, 1 << 20, 5000), (32, 7, 3000), (4, (1 << 30) - 4096, 4096)])
+def test_sobol_points_bit_exact(hp, d, k0, n):
+    rng = np.random.default_rng(d)
+    lb = rng.uniform(-50, 0, d)
+    ub = lb + rng.uniform(0.5, 80, d)
+    if d == 6:
+        lb[:], ub[:] = -5.12, 5.12
+    tab = hp.SobolTables(np.stack([lb, ub], 1))
+    ref = orc.sobol_points(orc.sobol_dirnums(d), k0, n, lb, ub)
+    soa = hp.sobol_points(tab, k0, n, "soa").cpu().numpy()
+    aos = hp.sobol_points(tab, k0, n, "aos").cpu().numpy()
+    assert np.array_equal(soa.T, ref)
+    assert np.array_equal(aos, ref)
+
+
+def test_sobol_points_match_scipy(hp):
+    from scipy.stats import qmc
+    d, n = 6, 2048
+    tab = hp.SobolTables([(-5.12, 5.12)] * d)
+    C = qmc.Sobol(d=d, scramble=False, seed=0).random(n)
+    for i in range(d):                      # the reference's scaling loop, _shgo.py:1446-1449
+        C[:, i] = C[:, i] * (5.12 - -5.12) + -5.12
+    assert np.array_equal(hp.sobol_points(tab, 0, n, "aos").cpu().numpy(), C)
+
+
+def test_empty_and_limits(hp):
+    tab = hp.SobolTables([(0, 1)] * 3)
+    assert hp.sobol_points(tab, 5, 0).shape == (3, 0)
+    f, feas = hp.eval_sobol(3, 0, tab, 0, 0)
+    assert f.numel() == 0
+    from shgo_b200 import _lib
+    with pytest.raises(_lib.Shgob200Error):
+        hp.sobol_points(tab, (1 << 30) - 10, 11)       # past the 30-bit sequence
+    with pytest.raises(_lib.Shgob200Error):
+        hp.eval_sobol(4, 0, tab, 0, 16)                # eggholder is 2-D only
+    with pytest.raises(_lib.Shgob200Error):
+        hp.eval_sobol(1, 1, tab, 0, 16)                # unregistered functor/constraint pair
+
+
+# ------------------------------------------------------------------------------------------
+EVAL_CASES = [
+    ("rosenbrock", None, [(0, 2)] * 5), ("rosenbrock", None, [(-2, 2)] * 12),
+    ("rastrigin", None, [(-5.12, 5.12)] * 6), ("rastrigin", None, [(-5.12, 5.12)] * 11),
+    ("ackley", None, [(-32.768, 32.768)] * 10), ("ackley", None, [(-32.768, 32.768)] * 3),
+    ("styblinski_tang", None, [(-5, 5)] * 8), ("styblinski_tang", None, [(-5, 5)] * 3),
+    ("eggholder", None, [(-512, 512)] * 2),
+    ("cattle_feed", None, [(0, 1.0)] * 4), ("cattle_feed", "cattle_feed", [(0, 1.0)] * 4),
+    ("sphere", None, [(-1, 6)] * 4), ("sphere", "sum_le_6", [(-1, 6)] * 2),
+]
+
+
+@pytest.mark.parametrize("functor,gset,bounds", EVAL_CASES)
+def test_eval_sobol_vs_oracle(hp, functor, gset, bounds):
+    fid, gid = _ids(functor, gset)
+    b = np.array(bounds, float)
+    d = len(bounds)
+    tab = hp.SobolTables(bounds)
+    sv = orc.sobol_dirnums(d)
+    for k0, n in [(0, 20000), (777, 4097)]:
+        f, feas = hp.eval_sobol(fid, gid, tab, k0, n)
+        fo, feo = orc.sobol_eval(sv, functor, gset, k0, n, b[:, 0], b[:, 1])
+        f, feas = f.cpu().numpy(), feas.cpu().numpy()
+        assert np.array_equal(feas, feo)
+        if functor in DEVICE_BIT_EXACT:
+            assert np.array_equal(f, fo)
+        else:
+            _close(f, fo)
+        # same evaluation on materialised points
+        x = hp.sobol_points(tab, k0, n, "soa")
+        f2, feas2 = hp.eval_points(fid, gid, x)
+        assert torch.equal(f2.cpu(), torch.from_numpy(f)) and np.array_equal(feas2.cpu().numpy(), feas)
+
+
+def test_eval_matches_numpy_callables(hp):
+    """device f vs the reference-side numpy callables (what compute_sfield would call)."""
+    from shgo_b200 import functors as F
+    for fn, bounds in [(F.rosenbrock, [(0, 2)] * 5), (F.rastrigin, [(-5.12, 5.12)] * 6),
+                       (F.ackley, [(-32.768, 32.768)] * 10), (F.styblinski_tang, [(-5, 5)] * 8),
+                       (F.eggholder, [(-512, 512)] * 2), (F.cattle_feed, [(0, 1.0)] * 4)]:
+        tab = hp.SobolTables(bounds)
+        n = 2000
+        x = hp.sobol_points(tab, 0, n, "aos").cpu().numpy()
+        f = hp.eval_sobol(fn.shgo_b200_functor, 0, tab, 0, n)[0].cpu().numpy()
+        ref = np.array([fn(xi) for xi in x])
+        if fn in (F.rosenbrock, F.cattle_feed):
+            assert np.array_equal(f, ref)
+        else:
+            _close(f, ref)
+
+
+def test_mask_infeasible(hp):
+    n = 10000
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal(n)
+    f[::17] = np.nan
+    g = rng.standard_normal((2, n))
+    g[0, ::13] = np.nan                      # NaN constraint value counts as feasible
+    ft, feas = hp.mask_infeasible(torch.from_numpy(f).cuda(), torch.from_numpy(g).cuda())
+    ok = ~((g[0] < 0) | (g[1] < 0))
+    ref = np.where(ok & ~np.isnan(f), f, np.inf)
+    assert np.array_equal(ft.cpu().numpy(), ref)
+    assert np.array_equal(feas.cpu().numpy().astype(bool), ok)
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SOBOL_CASES)
+def test_golden_sobol_case(hp, name):
+    g = load_golden(name)
+    functor, gset = str(g["functor"]), gset_of(g)
+    fid, gid = _ids(functor, gset)
+    bounds, n = g["bounds"], int(g["n"])
+    tab = hp.SobolTables(bounds)
+    # points handed to qhull
+    assert np.array_equal(hp.sobol_points(tab, 0, n, "aos").cpu().numpy(), g["points"])
+    # vf_to_vv on the very simplices the reference consumed
+    simp = torch.from_numpy(g["simplices"].astype(np.int32)).cuda()
+    row_ptr, col = hp.csr_from_simplices(simp, n)
+    rp_o, col_o = orc.vf_to_vv(g["simplices"].astype(np.int32), n)
+    assert np.array_equal(row_ptr.cpu().numpy(), rp_o)
+    assert np.array_equal(col.cpu().numpy(), col_o)
+    rp = row_ptr.cpu().numpy()
+    u = np.repeat(np.arange(n), np.diff(rp))
+    e = np.stack([u, col.cpu().numpy()], 1)
+    assert np.array_equal(e[e[:, 0] < e[:, 1]], g["edges"].astype(np.int64))
+    # evaluate + mask
+    f, feas = hp.eval_sobol(fid, gid, tab, 0, n)
+    present = np.diff(rp) > 0
+    fh = f.cpu().numpy()
+    assert np.array_equal(feas.cpu().numpy()[present], g["feasible"][present])
+    if functor in BIT_EXACT_F:
+        assert np.array_equal(fh[present], g["f"][present])
+    else:
+        _close(fh[present], g["f"][present])
+    # classify + pool + bookkeeping
+    is_min = hp.star_csr(row_ptr, col, f)
+    idx, cnt = hp.compact_pool(is_min)
+    pool = idx[: int(cnt.item())].cpu().numpy()
+    assert np.array_equal(pool, g["pool"])
+    assert int(hp.count_nfev(row_ptr, feas).item()) == int(g["nfev"])
+    fo, _ = orc.eval_points(functor, gset, g["points"])
+    pres_t = torch.from_numpy(present.astype(np.uint8)).cuda()
+    i_dev, v_dev = hp.argmin(f, pres_t)
+    i_or = orc.argmin(fh, present.astype(np.uint8))
+    assert i_dev == i_or and v_dev == fh[i_or]
+
+
+def test_star_sharded_rows_and_random_graphs(hp):
+    rng = np.random.default_rng(11)
+    for n, S, dp1 in [(1000, 5000, 4), (50, 7, 3), (4096, 60000, 7), (300, 299, 2), (10, 0, 3)]:
+        simp = rng.integers(0, n, size=(S, dp1)).astype(np.int32)
+        rp_o, col_o = orc.vf_to_vv(simp, n)
+        row_ptr, col = hp.csr_from_simplices(torch.from_numpy(simp).cuda(), n)
+        assert np.array_equal(row_ptr.cpu().numpy(), rp_o)
+        assert np.array_equal(col.cpu().numpy(), col_o)
+        f = rng.standard_normal(n)
+        f[rng.integers(0, n, n // 10)] = np.inf
+        f[rng.integers(0, n, n // 10)] = f[rng.integers(0, n, n // 10)]     # exact ties
+        ft = torch.from_numpy(f).cuda()
+        ref = orc.star_csr(rp_o, col_o, f)
+        assert np.array_equal(hp.star_csr(row_ptr, col, ft).cpu().numpy(), ref)
+        for row0, rows in [(0, n // 3), (n // 3, n - n // 3), (n - 1, 1), (5, 0)]:
+            got = hp.star_csr(row_ptr, col, ft, row0, rows).cpu().numpy()
+            assert np.array_equal(got, ref[row0:row0 + rows])
+        idx, cnt = hp.compact_pool(torch.from_numpy(ref).cuda(), base=100)
+        assert np.array_equal(idx[: int(cnt.item())].cpu().numpy(), orc.compact_pool(ref) + 100)
+
+
+def test_star_skewed_degrees_fall_back_to_global_col(hp):
+    """one hub with ~20000 neighbours: the tile's slice exceeds the staging buffer"""
+    n = 30000
+    hub = np.stack([np.zeros(n - 1, np.int32), np.arange(1, n, dtype=np.int32)], 1)
+    chain = np.stack([np.arange(1, n - 1, dtype=np.int32), np.arange(2, n, dtype=np.int32)], 1)
+    simp = np.concatenate([hub, chain])
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal(n)
+    f[0] = -100.0
+    rp_o, col_o = orc.vf_to_vv(simp, n)
+    row_ptr, col = hp.csr_from_simplices(torch.from_numpy(simp).cuda(), n)
+    assert np.array_equal(col.cpu().numpy(), col_o)
+    got = hp.star_csr(row_ptr, col, torch.from_numpy(f).cuda()).cpu().numpy()
+    assert np.array_equal(got, orc.star_csr(rp_o, col_o, f)) and got[0] == 1
+
+
+def test_compact_and_argmin_edge_cases(hp):
+    z = torch.zeros(5000, dtype=torch.uint8, device="cuda")
+    idx, cnt = hp.compact_pool(z)
+    assert int(cnt.item()) == 0
+    o = torch.ones(4097, dtype=torch.uint8, device="cuda")
+    idx, cnt = hp.compact_pool(o, cap=10)
+    assert int(cnt.item()) == 4097 and idx[:10].tolist() == list(range(10))
+    f = torch.full((1000,), float("inf"), dtype=torch.float64, device="cuda")
+    assert hp.argmin(f) == (-1, float("inf"))
+    f[700] = 3.0
+    f[300] = 3.0
+    assert hp.argmin(f) == (300, 3.0)
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", LATTICE_CASES)
+def test_lattice_coords_and_star_vs_oracle(hp, name):
+    g = load_golden(name)
+    bounds = [tuple(b) for b in g["bounds"]]
+    d = len(bounds)
+    from shgo_b200 import lattice
+    rng = np.random.default_rng(1)
+    for gen in range(int(g["gens"]) + 1):
+        tab_h = lattice.coordinate_tables(bounds, gen)
+        assert np.array_equal(tab_h, orc.lattice_tables(bounds, gen))
+        tab = torch.from_numpy(tab_h).cuda()
+        nv, _ = orc.lattice_nvert(d, gen)
+        x = hp.lattice_coords(d, gen, tab, 0, nv).cpu().numpy().T
+        assert np.array_equal(x, orc.lattice_coords(bounds, gen))
+        assert {tuple(c) for c in x} == {tuple(c) for c in g[f"coords_g{gen}"]}
+        for trial in range(3):
+            f = rng.standard_normal(nv) if trial else np.sum(x ** 2, axis=1)
+            if trial == 2:
+                f[rng.integers(0, nv, nv // 5 + 1)] = np.inf
+            got = hp.lattice_star(d, gen, torch.from_numpy(f).cuda()).cpu().numpy()
+            assert np.array_equal(got, orc.lattice_star(d, gen, f)), (name, gen, trial)
+
+
+@pytest.mark.parametrize("name", SIMPLICIAL_POOL_CASES)
+def test_golden_simplicial_pools(hp, name):
+    g = load_golden(name)
+    functor, gset = str(g["functor"]), gset_of(g)
+    fid, gid = _ids(functor, gset)
+    bounds = [tuple(b) for b in g["bounds"]]
+    d = len(bounds)
+    from shgo_b200 import lattice
+    started = set()
+    for it in range(int(g["iters"])):
+        tab = torch.from_numpy(lattice.coordinate_tables(bounds, it)).cuda()
+        nv, _ = orc.lattice_nvert(d, it)
+        assert nv == int(g[f"nvert_{it}"])
+        f, feas = hp.lattice_eval(fid, gid, d, it, tab, 0, nv)
+        assert int(feas.sum().item()) == int(g[f"nfev_{it}"])
+        x = hp.lattice_coords(d, it, tab, 0, nv).cpu().numpy().T
+        fo, feo = orc.eval_points(functor, gset, x)
+        if functor in DEVICE_BIT_EXACT:
+            assert np.array_equal(f.cpu().numpy(), fo)
+        else:
+            _close(f.cpu().numpy(), fo)
+        is_min = hp.lattice_star(d, it, f).cpu().numpy()
+        pool = {tuple(x[i]) for i in np.flatnonzero(is_min)} - started
+        ref = {tuple(p) for p in g[f"pool_x_{it}"]}
+        assert pool == ref, (name, it)
+        started |= ref
+
+
+def test_lattice_10d_generation1_vs_oracle(hp):
+    """config 3 scale-down: 10-D Ackley lattice, generation 1 (60 073 vertices, degree <= 59 048)"""
+    d, gen = 10, 1
+    bounds = [(-32.768, 32.768)] * d
+    from shgo_b200 import lattice
+    tab = torch.from_numpy(lattice.coordinate_tables(bounds, gen)).cuda()
+    nv, _ = orc.lattice_nvert(d, gen)
+    f, _ = hp.lattice_eval(orc.FUNCTOR_IDS["ackley"], 0, d, gen, tab, 0, nv)
+    fh = f.cpu().numpy()
+    x = orc.lattice_coords(bounds, gen)
+    _close(fh, orc.eval_points("ackley", None, x)[0])
+    got = hp.lattice_star(d, gen, f).cpu().numpy()
+    assert np.array_equal(got, orc.lattice_star(d, gen, fh))
+    # sharded vertex ranges give the same flags
+    a = hp.lattice_star(d, gen, f, 0, 30000).cpu().numpy()
+    b = hp.lattice_star(d, gen, f, 30000, nv - 30000).cpu().numpy()
+    assert np.array_equal(np.concatenate([a, b]), got)
+
+
+# ------------------------------------------------------------------------------------------
+def test_full_size_properties(hp):
+    """BASELINE sizes (config 5 at 2^24): properties that do not need an O(n) CPU pass in Python,
+    plus oracle spot checks on shards."""
+    n, d = 1 << 24, 8
+    bounds = [(-5.0, 5.0)] * d
+    tab = hp.SobolTables(bounds)
+    f, feas = hp.eval_sobol(orc.FUNCTOR_IDS["styblinski_tang"], 0, tab, 0, n)
+    sv = orc.sobol_dirnums(d)
+    b = np.array(bounds)
+    for k0 in (0, 5_000_001, n - 65536):
+        fo, _ = orc.sobol_eval(sv, "styblinski_tang", None, k0, 65536, b[:, 0], b[:, 1])
+        assert np.array_equal(f[k0:k0 + 65536].cpu().numpy(), fo)
+    # shard-additivity: evaluating [k0, k0+m) alone equals the slice of the whole
+    f2, _ = hp.eval_sobol(orc.FUNCTOR_IDS["styblinski_tang"], 0, tab, 3_333_333, 1_000_000)
+    assert torch.equal(f2, f[3_333_333:4_333_333])
+    row_ptr, col = hp.hypercube_csr(n)
+    is_min = hp.star_csr(row_ptr, col, f)
+    # definition check on the device: min over neighbours, strict
+    m = 24
+    nbmin = torch.full((n,), float("inf"), dtype=torch.float64, device="cuda")
+    i = torch.arange(n, device="cuda")
+    for j in range(m):
+        nbmin = torch.minimum(nbmin, f[i ^ (1 << j)])
+    assert torch.equal(is_min.bool(), f < nbmin)
+    idx, cnt = hp.compact_pool(is_min)
+    c = int(cnt.item())
+    assert c == int(is_min.sum().item())
+    pool = idx[:c]
+    assert bool((pool[1:] > pool[:-1]).all()) and bool(is_min[pool].all())
+    # oracle on a row range of the same graph
+    rp_h, col_h = orc.hypercube_csr(1 << 16)
+    fh = f[: 1 << 16].cpu().numpy()
+    sub = hp.star_csr(torch.from_numpy(rp_h).cuda(), torch.from_numpy(col_h).cuda(),
+                      f[: 1 << 16].contiguous()).cpu().numpy()
+    assert np.array_equal(sub, orc.star_csr(rp_h, col_h, fh))
+
+
+def test_host_buffer_iteration_matches_device_path(hp):
+    import ctypes
+    from shgo_b200 import _lib
+    n, d = 1 << 16, 6
+    bounds = np.array([(-5.12, 5.12)] * d)
+    sv = orc.sobol_dirnums(d)
+    rp, col = orc.hypercube_csr(n)
+    fo, feo = orc.sobol_eval(sv, "rastrigin", None, 0, n, bounds[:, 0], bounds[:, 1])
+    ctx = ctypes.c_void_p()
+    _lib.call("shgo_b200_ctx_create", 0, ctypes.byref(ctx))
+    try:
+        pool = np.empty(n, np.int64)
+        cnt, nfev = ctypes.c_uint64(), ctypes.c_uint64()
+        fout = np.empty(n)
+        lb, ub = bounds[:, 0].copy(), bounds[:, 1].copy()
+        for _ in range(2):
+            _lib.call("shgo_b200_iterate_sobol_host", ctx, 1, 0, d, 0, n, sv.ctypes.data, lb.ctypes.data,
+                      ub.ctypes.data, rp.ctypes.data, col.ctypes.data, pool.ctypes.data, n,
+                      ctypes.byref(cnt), ctypes.byref(nfev), fout.ctypes.data)
+        _close(fout, fo)
+        ref_pool = orc.compact_pool(orc.star_csr(rp, col, fout))
+        assert np.array_equal(pool[: cnt.value], ref_pool)
+        assert nfev.value == n
+    finally:
+        _lib.lib().shgo_b200_ctx_destroy(ctx)

@@ -1,0 +1,75 @@
+"""CPU-side checks of the product's host logic (no GPU, no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from shgo_b200 import _lib, build
+    build.build_library()
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "shgo_b200.h")).read()
+    declared = set(re.findall(r"SHGO_B200_API[^;]*?\b(shgo_b200_\w+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.shgo_b200_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from shgo_b200 import _lib
+    with pytest.raises(_lib.Shgob200Error):
+        _lib.call("shgo_b200_device_info", 0, None, None, None, None)
+    from shgo_b200 import hotpath
+    with pytest.raises(RuntimeError):
+        hotpath.SobolTables([(0, 1)] * 3)
+
+
+def test_direction_numbers_match_scipy():
+    from scipy.stats import qmc
+    from shgo_b200 import _sobol
+    for d in (1, 2, 5, 8, 10, 41, 333, 1024):
+        ref = np.asarray(qmc.Sobol(d=d, scramble=False, seed=0)._sv, np.uint32)
+        assert np.array_equal(_sobol.direction_numbers(d), ref), d
+
+
+def test_functor_registry():
+    from scipy.optimize import rosen
+    from scipy._lib._util import _FunctionWrapper  # what SHGO wraps func in (_shgo.py:14,515)
+    from shgo_b200 import functors as F
+    assert F.functor_id(rosen) == F.F_ROSENBROCK
+    assert F.functor_id(F.rastrigin) == F.F_RASTRIGIN
+    assert F.functor_id(_FunctionWrapper(F.ackley, ())) == F.F_ACKLEY
+    assert F.functor_id(_FunctionWrapper(F.ackley, (1,))) is None      # extra args: not the functor
+    assert F.functor_id(lambda x: 0.0) is None
+    assert F.constraint_set_id(None) == F.G_NONE
+    assert F.constraint_set_id((F.cattle_feed_g1, F.cattle_feed_g2)) == F.G_CATTLE_FEED
+    assert F.constraint_set_id((F.cattle_feed_g2, F.cattle_feed_g1)) is None
+    assert F.constraint_set_id((F.cattle_feed_g1,)) is None
+    assert F.constraint_set_id((F.sum_le_6,)) == F.G_SUM_LE_6
+    x = np.array([0.3, -1.2, 2.5, 0.7])
+    assert F.rosenbrock(x) == rosen(x)
+
+
+def test_registered_numpy_callables_agree_with_oracle_definitions():
+    """The product's numpy callables and the oracle's are the same functions."""
+    from oracle import oracle as orc
+    from shgo_b200 import functors as F
+    rng = np.random.default_rng(0)
+    for name, fn in [("rosenbrock", F.rosenbrock), ("rastrigin", F.rastrigin), ("ackley", F.ackley),
+                     ("styblinski_tang", F.styblinski_tang), ("sphere", F.sphere)]:
+        x = rng.uniform(-3, 3, 6)
+        assert fn(x) == orc.NP_OBJECTIVES[name](x)
+    x = rng.uniform(0, 1, 4)
+    assert F.cattle_feed(x) == orc.np_cattle_feed(x)
+    assert F.cattle_feed_g2(x) == orc.np_cattle_g2(x)
+    x = rng.uniform(-512, 512, 2)
+    assert F.eggholder(x) == orc.np_eggholder(x)
