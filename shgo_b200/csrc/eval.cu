@@ -291,9 +291,9 @@ int shgo_b200_sobol_fill(const uint32_t *sv, int d, uint64_t k0, uint64_t n, con
                          const double *ub, double *x, uint64_t ld, int layout, void *stream)
 {
     if (int rc = check_sobol_args(sv, d, k0, n, lb, ub)) return rc;
+    if (n == 0) return SHGO_B200_OK;
     SHGO_REQUIRE(x, "null output");
     SHGO_REQUIRE(layout == 1 || ld >= n, "ld < n");
-    if (n == 0) return SHGO_B200_OK;
     constexpr int P = 4;
     typename SobolSrc<P>::Params sp{sv, lb, ub, k0, n, d};
     size_t smem = SobolSrc<P>::smem_bytes(d);
@@ -311,8 +311,8 @@ int shgo_b200_eval_sobol(int functor, int gset, int d, uint64_t k0, uint64_t n, 
                          void *stream)
 {
     if (int rc = check_sobol_args(sv, d, k0, n, lb, ub)) return rc;
-    SHGO_REQUIRE(f, "null output");
     if (n == 0) return SHGO_B200_OK;
+    SHGO_REQUIRE(f, "null output");
     return dispatch_eval<SobolSrc>(functor, gset, d, n, SobolMk{sv, lb, ub, k0, n, d}, SobolSmem{d},
                                    f, feasible, as_stream(stream));
 }
@@ -320,10 +320,10 @@ int shgo_b200_eval_sobol(int functor, int gset, int d, uint64_t k0, uint64_t n, 
 int shgo_b200_eval_points(int functor, int gset, int d, uint64_t n, const double *x_soa, uint64_t ld,
                           double *f, uint8_t *feasible, void *stream)
 {
-    SHGO_REQUIRE(x_soa && f, "null pointer");
     SHGO_REQUIRE(d >= 1 && d <= kMaxDim, "dimension %d outside 1..%d", d, kMaxDim);
-    SHGO_REQUIRE(ld >= n, "ld < n");
     if (n == 0) return SHGO_B200_OK;
+    SHGO_REQUIRE(x_soa && f, "null pointer");
+    SHGO_REQUIRE(ld >= n, "ld < n");
     return dispatch_eval<SoaSrc>(functor, gset, d, n, SoaMk{x_soa, ld, n, d}, ZeroSmem{}, f, feasible,
                                  as_stream(stream));
 }

@@ -170,7 +170,10 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(uint64_t *sums, uint64_
         carry += chunk_total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = carry;
+    if (threadIdx.x == 0) {
+        *total = carry;
+        sums[nb] = carry;  // offset of a virtual block past the end (row_ptr[n] when n % 4096 == 0)
+    }
 }
 
 // pool compaction, pass 3: ascending indices of the non-zero flags
@@ -404,10 +407,9 @@ extern "C" {
 int shgo_b200_star_csr(const int64_t *row_ptr, const int32_t *col, const double *f, uint64_t row0,
                        uint64_t rows, uint8_t *is_min, void *stream)
 {
-    SHGO_REQUIRE(row_ptr && f && is_min, "null pointer");
-    SHGO_REQUIRE(col || rows == 0, "null col");
-    SHGO_REQUIRE((reinterpret_cast<uintptr_t>(col) & 15) == 0, "col must be 16-byte aligned");
     if (rows == 0) return SHGO_B200_OK;
+    SHGO_REQUIRE(row_ptr && f && is_min, "null pointer");
+    SHGO_REQUIRE((reinterpret_cast<uintptr_t>(col) & 15) == 0, "col must be 16-byte aligned");
     int occ = 0;
     SHGO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, star_csr_kernel, kStarThreads, 0));
     if (occ < 1) occ = 1;
@@ -497,7 +499,8 @@ int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, 
                                                                 deg, bad);
     block_sum_kernel<uint32_t><<<(unsigned)nb, kScanThreads, 0, st>>>(deg, n, sums);
     scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, nnz);
-    rowptr_kernel<<<(unsigned)nb, kScanThreads, 0, st>>>(deg, n, sums, row_ptr);
+    // n+1 outputs: one more block when n is a multiple of the block size
+    rowptr_kernel<<<(unsigned)(n / kScanBlock + 1), kScanThreads, 0, st>>>(deg, n, sums, row_ptr);
     if (S > 0) {
         edge_fill_kernel<<<grid_for(slots, 256, 8), 256, 0, st>>>(table, slots, row_ptr, cursor, col_tmp);
         row_sort_kernel<<<grid_for(n * 32, 256, 8), 256, 0, st>>>(row_ptr, n, col_tmp, col);
