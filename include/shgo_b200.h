@@ -120,7 +120,15 @@ SHGO_B200_API int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_
  * call classifies rows [row0, row0+rows) -- the shard of one GPU.
  */
 SHGO_B200_API int shgo_b200_star_csr(const int64_t *row_ptr, const int32_t *col, const double *f,
-                       uint64_t row0, uint64_t rows, uint8_t *is_min, void *stream);
+                       uint64_t row0, uint64_t rows, uint64_t nnz_hint, uint8_t *is_min,
+                       void *stream);
+/* same, and in the same pass *nfev = number of classified rows that exist (non-empty) and are
+ * feasible (feasible[r], indexed like is_min, may be NULL): the reference's HC.V.nfev
+ * (_vertex.py:184,347).  nnz_hint (both calls): number of col entries of the classified rows, used
+ * only to size the shared-memory staging buffers; 0 = unknown. */
+SHGO_B200_API int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t *col, const double *f,
+                            const uint8_t *feasible, uint64_t row0, uint64_t rows,
+                            uint64_t nnz_hint, uint8_t *is_min, uint64_t *nfev, void *stream);
 
 /* ---- a7: pool extraction ----------------------------------------------------------------------------
  * Replaces the scan over HC.V.cache in SHGO.minimizers (reference _shgo.py:1109-1157):

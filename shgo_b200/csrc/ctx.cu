@@ -138,11 +138,12 @@ int shgo_b200_iterate_sobol_host(shgo_b200_ctx *c, int functor, int gset, int d,
                                       c->feas, c->compute))
         return rc;
     SHGO_CUDA_TRY(cudaStreamWaitEvent(c->compute, c->uploaded, 0));
-    if (int rc = shgo_b200_star_csr(c->row_ptr, c->col, c->f, 0, n, c->is_min, c->compute)) return rc;
+    if (int rc = shgo_b200_star_csr_nfev(c->row_ptr, c->col, c->f, c->feas, 0, n, nnz, c->is_min,
+                                         c->scalars + 1, c->compute))
+        return rc;
     if (int rc = shgo_b200_compact_pool(c->is_min, n, (int64_t)0, c->pool, pool_cap, c->scalars, c->tmp,
                                         c->cap_tmp, c->compute))
         return rc;
-    if (int rc = shgo_b200_count_nfev(c->row_ptr, c->feas, n, c->scalars + 1, c->compute)) return rc;
     SHGO_CUDA_TRY(cudaMemcpyAsync(c->h_scalars, c->scalars, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                                   c->compute));
     if (f_out)

@@ -7,64 +7,102 @@ namespace shgo_b200 {
 // =============================================================================================
 // K4: star test over an explicit CSR  (reference _vertex.py:144-151, 422-426)
 //
-// A CTA owns a tile of 256 consecutive rows.  The tile's slice of `col` is one contiguous range
-// col[row_ptr[r0] .. row_ptr[r0+256]) and is staged into shared memory with coalesced 16-byte
-// loads, so `col` (4*nnz bytes, the bulk of the compulsory traffic) streams from HBM exactly once
-// at full sector efficiency.  Then one thread walks one row: neighbour ids come from shared
-// memory, neighbour f values are gathered through L1/L2 with ld.global.nc, four at a time, and a
-// row stops as soon as one neighbour is not strictly larger (the reference's all() also
-// short-circuits) -- on average only ~H(deg) gathers per row are issued.  Mapping thread <-> row
-// (not warp <-> row) makes the gathers of a warp hit neighbouring sectors whenever consecutive
-// rows have "parallel" neighbour lists, which is the case for lattice-like graphs.
-// Rows whose tile slice exceeds the staging buffer fall back to reading `col` from global memory.
+// One WARP owns a tile of 32 consecutive rows; one thread walks one row.  The tile's slice of
+// `col` is the contiguous range col[row_ptr[r0] .. row_ptr[r0+32]) and is staged into the warp's
+// private shared-memory slice with 16-byte cp.async (LDGSTS) copies, so `col` -- 4*nnz bytes, the
+// bulk of the compulsory traffic -- streams from HBM exactly once at full sector efficiency and
+// without register staging.  Warps never wait on one another (only __syncwarp), so the 48 resident
+// warps of an SM are naturally staggered between "streaming col" and "gathering f".
+// The walk itself: neighbour ids come from shared memory, neighbour f values are gathered through
+// L1/L2 with ld.global.nc in rounds of 4, then 8, 8, ...; a
+// row stops as soon as one neighbour is not strictly larger (the reference's all() short-circuits
+// as well).  On a random field a row
+// survives k neighbours with probability 1/(k+1), so ~7 gathers per row are issued instead of deg,
+// and the dependent-latency chain of a warp is at most 1 + ceil((deg-4)/8) rounds.
+// Mapping thread <-> row (not warp <-> row) makes the gathers of a warp hit neighbouring sectors
+// whenever consecutive rows have "parallel" neighbour lists (lattice-like graphs).
+// A tile whose slice exceeds the warp's staging buffer reads `col` from global memory instead.
+// The same pass counts nfev (rows that exist and are feasible, reference _vertex.py:184,347).
 // =============================================================================================
-constexpr int kStarThreads = 256;
-constexpr int kStarCap = 12288;  // int32 entries staged per tile (48 KB)
+constexpr int kStarWarps = 8;
+constexpr int kStarThreads = kStarWarps * 32;
 
-__global__ void __launch_bounds__(kStarThreads)
-star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                const double *__restrict__ f, uint64_t row0, uint64_t rows,
-                uint8_t *__restrict__ is_min)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
-    __shared__ __align__(16) int32_t scol[kStarCap];
-    const uint64_t ntiles = (rows + kStarThreads - 1) / kStarThreads;
-    const int t = threadIdx.x;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t lr0 = tile * kStarThreads;
-        const uint64_t nrow = rows - lr0 < (uint64_t)kStarThreads ? rows - lr0 : kStarThreads;
-        const bool valid = (uint64_t)t < nrow;
-        const uint64_t r = row0 + lr0 + (valid ? t : 0);
-        const int64_t b = row_ptr[r], e = row_ptr[r + 1];
-        const double fv = ld_nc_f64(f + r);
-        const int64_t s0 = row_ptr[row0 + lr0], s1 = row_ptr[row0 + lr0 + nrow];
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// One round of the row walk on the staged slice: the next W neighbours (32-bit local indices; the
+// tail of a row is handled by clamping, so a short row simply re-tests its last neighbour instead
+// of paying for per-entry predicates and +inf selects).
+template <int W>
+__device__ __forceinline__ bool star_round(const int32_t *__restrict__ sc, const double *__restrict__ f,
+                                           double fv, int &k, int last)
+{
+    int32_t nb[W];
+    double fn[W];
+#pragma unroll
+    for (int u = 0; u < W; ++u) nb[u] = sc[min(k + u, last)];
+#pragma unroll
+    for (int u = 0; u < W; ++u) fn[u] = ld_nc_f64(f + nb[u]);
+    bool ok = true;
+#pragma unroll
+    for (int u = 0; u < W; ++u) ok = ok && (fv < fn[u]);
+    k += W;
+    return ok;
+}
+
+__global__ void __launch_bounds__(kStarThreads, 6)
+star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                const double *__restrict__ f, const uint8_t *__restrict__ feasible, uint64_t row0,
+                uint64_t rows, int cap_w, uint8_t *__restrict__ is_min,
+                unsigned long long *__restrict__ nfev)
+{
+    extern __shared__ __align__(16) int32_t star_smem[];
+    const int lane = threadIdx.x & 31;
+    int32_t *sc = star_smem + (threadIdx.x >> 5) * cap_w;
+    const uint64_t ntiles = (rows + 31) >> 5;
+    const uint64_t gw = ((uint64_t)blockIdx.x * kStarThreads + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * kStarThreads) >> 5;
+    unsigned present_feasible = 0;
+    for (uint64_t tile = gw; tile < ntiles; tile += nw) {
+        const uint64_t lr = (tile << 5) + lane;
+        const bool valid = lr < rows;
+        const uint64_t r = row0 + (valid ? lr : rows);  // invalid lanes: empty row at the end
+        const int64_t b = row_ptr[r];
+        const int64_t e = valid ? row_ptr[r + 1] : b;
+        const double fv = valid ? ld_nc_f64(f + r) : 0.0;
+        const int64_t s0 = __shfl_sync(0xffffffffu, b, 0), s1 = __shfl_sync(0xffffffffu, e, 31);
         const int64_t s0a = s0 & ~(int64_t)3;
-        const bool staged = (s1 - s0a) <= kStarCap;
-        if (staged) {
-            const int64_t nvec = (s1 - s0a) >> 2;  // full 16-byte vectors inside the slice
-            const int4 *src = reinterpret_cast<const int4 *>(col + s0a);
-            int4 *dst = reinterpret_cast<int4 *>(scol);
-            for (int64_t v = t; v < nvec; v += kStarThreads) dst[v] = __ldg(src + v);
-            for (int64_t k = s0a + (nvec << 2) + t; k < s1; k += kStarThreads)
-                scol[k - s0a] = __ldg(col + k);
-        }
-        __syncthreads();
         bool ok = valid && e > b;
-        if (staged) {
-            for (int64_t k = b; k < e && ok; k += 4) {
-                int32_t nb[4];
-                double fn[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) nb[u] = k + u < e ? scol[k + u - s0a] : -1;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) fn[u] = nb[u] >= 0 ? ld_nc_f64(f + nb[u]) : pos_inf();
-#pragma unroll
-                for (int u = 0; u < 4; ++u) ok = ok && (fv < fn[u]);
-            }
+        if (nfev != nullptr && ok && (feasible == nullptr || feasible[lr])) ++present_feasible;
+        if (s1 - s0a <= cap_w) {
+            const int len = (int)(s1 - s0a);
+            const int nvec = len >> 2;  // full 16-byte vectors inside the slice
+            const int32_t *src = col + s0a;
+            for (int v = lane; v < nvec; v += 32) cp_async16(sc + (v << 2), src + (v << 2));
+            for (int k = (nvec << 2) + lane; k < len; k += 32) sc[k] = __ldg(src + k);
+            cp_async_wait_all();
+            __syncwarp();
+            int k = (int)(b - s0a);
+            const int le = (int)(e - s0a), last = le - 1;
+            if (ok) ok = star_round<4>(sc, f, fv, k, last);
+            while (ok && k < le) ok = star_round<8>(sc, f, fv, k, last);
         } else {
             for (int64_t k = b; k < e && ok; ++k) ok = fv < ld_nc_f64(f + __ldg(col + k));
         }
-        if (valid) is_min[lr0 + t] = ok ? 1 : 0;
-        __syncthreads();
+        if (valid) is_min[lr] = ok ? 1 : 0;
+        __syncwarp();  // the slice is rewritten by the next tile
+    }
+    if (nfev != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) present_feasible += __shfl_down_sync(0xffffffffu, present_feasible, o);
+        if (lane == 0 && present_feasible) atomicAdd(nfev, (unsigned long long)present_feasible);
     }
 }
 
@@ -404,22 +442,51 @@ using namespace shgo_b200;
 
 extern "C" {
 
-int shgo_b200_star_csr(const int64_t *row_ptr, const int32_t *col, const double *f, uint64_t row0,
-                       uint64_t rows, uint8_t *is_min, void *stream)
+static int launch_star(const int64_t *row_ptr, const int32_t *col, const double *f,
+                       const uint8_t *feasible, uint64_t row0, uint64_t rows, uint64_t nnz_hint,
+                       uint8_t *is_min, uint64_t *nfev, cudaStream_t st)
 {
+    if (nfev) SHGO_CUDA_TRY(cudaMemsetAsync(nfev, 0, sizeof(uint64_t), st));
     if (rows == 0) return SHGO_B200_OK;
     SHGO_REQUIRE(row_ptr && f && is_min, "null pointer");
     SHGO_REQUIRE((reinterpret_cast<uintptr_t>(col) & 15) == 0, "col must be 16-byte aligned");
+    // staging slice per warp: 32 rows * ~1.25 * mean degree (+ alignment slack), 16-byte multiple
+    double mean_deg = nnz_hint ? (double)nnz_hint / (double)rows : 32.0;
+    long cap = (long)(mean_deg * 32.0 * 1.125) + 16;
+    if (cap < 256) cap = 256;
+    if (cap > 6144) cap = 6144;  // 24 KB per warp at most (1 CTA of 8 warps per SM)
+    cap = (cap + 63) & ~63L;
+    const size_t smem = (size_t)cap * kStarWarps * sizeof(int32_t);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        SHGO_CUDA_TRY(cudaFuncSetAttribute(star_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
+        configured = 200 * 1024;
+    }
     int occ = 0;
-    SHGO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, star_csr_kernel, kStarThreads, 0));
+    SHGO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, star_csr_kernel, kStarThreads, smem));
     if (occ < 1) occ = 1;
     uint64_t tiles = (rows + kStarThreads - 1) / kStarThreads;
     uint64_t grid = (uint64_t)sm_count() * occ;
     if (grid > tiles) grid = tiles;
-    star_csr_kernel<<<(unsigned)grid, kStarThreads, 0, as_stream(stream)>>>(row_ptr, col, f, row0, rows,
-                                                                          is_min);
+    star_csr_kernel<<<(unsigned)grid, kStarThreads, smem, st>>>(
+        row_ptr, col, f, feasible, row0, rows, (int)cap, is_min, reinterpret_cast<unsigned long long *>(nfev));
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;
+}
+
+int shgo_b200_star_csr(const int64_t *row_ptr, const int32_t *col, const double *f, uint64_t row0,
+                       uint64_t rows, uint64_t nnz_hint, uint8_t *is_min, void *stream)
+{
+    return launch_star(row_ptr, col, f, nullptr, row0, rows, nnz_hint, is_min, nullptr, as_stream(stream));
+}
+
+int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t *col, const double *f,
+                            const uint8_t *feasible, uint64_t row0, uint64_t rows, uint64_t nnz_hint,
+                            uint8_t *is_min, uint64_t *nfev, void *stream)
+{
+    SHGO_REQUIRE(nfev, "null nfev");
+    return launch_star(row_ptr, col, f, feasible, row0, rows, nnz_hint, is_min, nfev, as_stream(stream));
 }
 
 size_t shgo_b200_compact_workspace(uint64_t n)

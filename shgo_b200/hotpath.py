@@ -125,12 +125,20 @@ def csr_from_simplices(simplices, n):
     return row_ptr, col[: int(nnz.item())]
 
 
-def star_csr(row_ptr, col, f, row0=0, rows=None, is_min=None):
+def star_csr(row_ptr, col, f, row0=0, rows=None, is_min=None, feasible=None, nfev=None):
+    """Star test of rows [row0, row0+rows).  With `nfev` (1-element int64 tensor) the same pass
+    also counts the rows that exist and are feasible (`feasible` indexed like is_min)."""
     n = row_ptr.numel() - 1
     rows = n - row0 if rows is None else rows
     if is_min is None:
         is_min = torch.empty(rows, dtype=torch.uint8, device=f.device)
-    _lib.call("shgo_b200_star_csr", _ptr(row_ptr), _ptr(col), _ptr(f), row0, rows, _ptr(is_min), _stream())
+    hint = col.numel() if rows == n else 0
+    if nfev is None:
+        _lib.call("shgo_b200_star_csr", _ptr(row_ptr), _ptr(col), _ptr(f), row0, rows, hint,
+                  _ptr(is_min), _stream())
+    else:
+        _lib.call("shgo_b200_star_csr_nfev", _ptr(row_ptr), _ptr(col), _ptr(f), _ptr(feasible), row0,
+                  rows, hint, _ptr(is_min), _ptr(nfev), _stream())
     return is_min
 
 

@@ -181,6 +181,9 @@ def test_golden_sobol_case(hp, name):
     pool = idx[: int(cnt.item())].cpu().numpy()
     assert np.array_equal(pool, g["pool"])
     assert int(hp.count_nfev(row_ptr, feas).item()) == int(g["nfev"])
+    nf = torch.zeros(1, dtype=torch.int64, device="cuda")       # fused star + nfev pass
+    is_min2 = hp.star_csr(row_ptr, col, f, feasible=feas, nfev=nf)
+    assert torch.equal(is_min2, is_min) and int(nf.item()) == int(g["nfev"])
     fo, _ = orc.eval_points(functor, gset, g["points"])
     pres_t = torch.from_numpy(present.astype(np.uint8)).cuda()
     i_dev, v_dev = hp.argmin(f, pres_t)
