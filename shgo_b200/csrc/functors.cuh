@@ -163,7 +163,7 @@ struct Ackley {
 // ~1e-15 relative to the term magnitudes (tests pin 1e-12) and bit-for-bit with the oracle's C
 // restatement of the same chain.
 struct StyblinskiTang {
-    static constexpr int P = 4;
+    static constexpr int P = 8;
     static bool dim_ok(int d) { return d >= 1; }
     template <class Src>
     static __device__ __forceinline__ void run(Src &src, int d, double (&f)[P], uint32_t &feas)

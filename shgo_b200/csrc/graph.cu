@@ -11,14 +11,14 @@ namespace shgo_b200 {
 // `col` is the contiguous range col[row_ptr[r0] .. row_ptr[r0+32]) and is staged into the warp's
 // private shared-memory slice with 16-byte cp.async (LDGSTS) copies, so `col` -- 4*nnz bytes, the
 // bulk of the compulsory traffic -- streams from HBM exactly once at full sector efficiency and
-// without register staging.  Warps never wait on one another (only __syncwarp), so the 48 resident
+// without register staging.  Warps never wait on one another (only __syncwarp), so the 40 resident
 // warps of an SM are naturally staggered between "streaming col" and "gathering f".
 // The walk itself: neighbour ids come from shared memory, neighbour f values are gathered through
-// L1/L2 with ld.global.nc in rounds of 4, then 8, 8, ...; a
-// row stops as soon as one neighbour is not strictly larger (the reference's all() short-circuits
-// as well).  On a random field a row
+// L1/L2 with ld.global.nc in rounds of 4, 8, then 16, 16, ...; a row stops as soon as one neighbour
+// is not strictly larger (the reference's all() short-circuits as well).  On a random field a row
 // survives k neighbours with probability 1/(k+1), so ~7 gathers per row are issued instead of deg,
-// and the dependent-latency chain of a warp is at most 1 + ceil((deg-4)/8) rounds.
+// while the widening rounds keep the dependent-latency chain of the few long-lived rows short
+// (measured: 4/8/16 beats 4/8/8 and 8/8/8 on lattice-like AND on random graphs, profiles/).
 // Mapping thread <-> row (not warp <-> row) makes the gathers of a warp hit neighbouring sectors
 // whenever consecutive rows have "parallel" neighbour lists (lattice-like graphs).
 // A tile whose slice exceeds the warp's staging buffer reads `col` from global memory instead.
@@ -57,7 +57,26 @@ __device__ __forceinline__ bool star_round(const int32_t *__restrict__ sc, const
     return ok;
 }
 
-__global__ void __launch_bounds__(kStarThreads, 6)
+struct StarMeta {  // what a lane knows about its row of a tile before the slice arrives
+    int64_t b, e;
+    double fv;
+    bool valid;
+};
+__device__ __forceinline__ StarMeta star_meta(const int64_t *__restrict__ row_ptr,
+                                              const double *__restrict__ f, uint64_t row0,
+                                              uint64_t rows, uint64_t tile, uint64_t ntiles, int lane)
+{
+    StarMeta m;
+    const uint64_t lr = (tile << 5) + lane;
+    m.valid = tile < ntiles && lr < rows;
+    const uint64_t r = row0 + (m.valid ? lr : rows);  // invalid lanes: empty row at the end
+    m.b = row_ptr[r];
+    m.e = m.valid ? row_ptr[r + 1] : m.b;
+    m.fv = m.valid ? ld_nc_f64(f + r) : 0.0;
+    return m;
+}
+
+__global__ void __launch_bounds__(kStarThreads, 5)
 star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                 const double *__restrict__ f, const uint8_t *__restrict__ feasible, uint64_t row0,
                 uint64_t rows, int cap_w, uint8_t *__restrict__ is_min,
@@ -70,29 +89,35 @@ star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__
     const uint64_t gw = ((uint64_t)blockIdx.x * kStarThreads + threadIdx.x) >> 5;
     const uint64_t nw = ((uint64_t)gridDim.x * kStarThreads) >> 5;
     unsigned present_feasible = 0;
+    // row_ptr / f of the NEXT tile are fetched while the current one is walked
+    StarMeta cur = star_meta(row_ptr, f, row0, rows, gw, ntiles, lane);
     for (uint64_t tile = gw; tile < ntiles; tile += nw) {
         const uint64_t lr = (tile << 5) + lane;
-        const bool valid = lr < rows;
-        const uint64_t r = row0 + (valid ? lr : rows);  // invalid lanes: empty row at the end
-        const int64_t b = row_ptr[r];
-        const int64_t e = valid ? row_ptr[r + 1] : b;
-        const double fv = valid ? ld_nc_f64(f + r) : 0.0;
+        const int64_t b = cur.b, e = cur.e;
+        const double fv = cur.fv;
+        const bool valid = cur.valid;
         const int64_t s0 = __shfl_sync(0xffffffffu, b, 0), s1 = __shfl_sync(0xffffffffu, e, 31);
         const int64_t s0a = s0 & ~(int64_t)3;
-        bool ok = valid && e > b;
-        if (nfev != nullptr && ok && (feasible == nullptr || feasible[lr])) ++present_feasible;
-        if (s1 - s0a <= cap_w) {
+        const bool staged = s1 - s0a <= cap_w;
+        if (staged) {
             const int len = (int)(s1 - s0a);
             const int nvec = len >> 2;  // full 16-byte vectors inside the slice
             const int32_t *src = col + s0a;
             for (int v = lane; v < nvec; v += 32) cp_async16(sc + (v << 2), src + (v << 2));
             for (int k = (nvec << 2) + lane; k < len; k += 32) sc[k] = __ldg(src + k);
+        }
+        cur = star_meta(row_ptr, f, row0, rows, tile + nw, ntiles, lane);
+        bool ok = valid && e > b;
+        if (nfev != nullptr && ok && (feasible == nullptr || feasible[lr])) ++present_feasible;
+        if (staged) {
             cp_async_wait_all();
             __syncwarp();
-            int k = (int)(b - s0a);
-            const int le = (int)(e - s0a), last = le - 1;
+            const int lb = (int)(b - s0a), le = (int)(e - s0a);
+            int k = lb;
+            const int last = le - 1;
             if (ok) ok = star_round<4>(sc, f, fv, k, last);
-            while (ok && k < le) ok = star_round<8>(sc, f, fv, k, last);
+            if (ok && k < le) ok = star_round<8>(sc, f, fv, k, last);
+            while (ok && k < le) ok = star_round<16>(sc, f, fv, k, last);
         } else {
             for (int64_t k = b; k < e && ok; ++k) ok = fv < ld_nc_f64(f + __ldg(col + k));
         }
@@ -457,19 +482,16 @@ static int launch_star(const int64_t *row_ptr, const int32_t *col, const double 
     if (cap > 6144) cap = 6144;  // 24 KB per warp at most (1 CTA of 8 warps per SM)
     cap = (cap + 63) & ~63L;
     const size_t smem = (size_t)cap * kStarWarps * sizeof(int32_t);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        SHGO_CUDA_TRY(cudaFuncSetAttribute(star_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           200 * 1024));
-        configured = 200 * 1024;
-    }
+    auto kern = star_csr_kernel;
+    if (smem > 48 * 1024)
+        SHGO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int occ = 0;
-    SHGO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, star_csr_kernel, kStarThreads, smem));
+    SHGO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kStarThreads, smem));
     if (occ < 1) occ = 1;
     uint64_t tiles = (rows + kStarThreads - 1) / kStarThreads;
     uint64_t grid = (uint64_t)sm_count() * occ;
     if (grid > tiles) grid = tiles;
-    star_csr_kernel<<<(unsigned)grid, kStarThreads, smem, st>>>(
+    kern<<<(unsigned)grid, kStarThreads, smem, st>>>(
         row_ptr, col, f, feasible, row0, rows, (int)cap, is_min, reinterpret_cast<unsigned long long *>(nfev));
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;
