@@ -113,6 +113,13 @@ SHGO_B200_API int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_
                                  int64_t *row_ptr, int32_t *col, uint64_t col_cap, uint64_t *nnz,
                                  void *tmp, size_t tmp_bytes, void *stream);
 
+/* Position (3*s + slot) at which vf_to_vv first touches each vertex while it walks the simplices
+ * (reference _complex.py:1064-1069), ~0 for vertices it never touches.  This is the insertion
+ * order of the reference's vertex cache (_vertex.py:304-317), i.e. the order in which
+ * SHGO.minimizers lists the pool (_shgo.py:1115-1152). */
+SHGO_B200_API int shgo_b200_first_seen(const int32_t *simplices, uint64_t S, int dp1, uint64_t n,
+                         uint64_t *first_seen, void *stream);
+
 /* ---- a6: star test ------------------------------------------------------------------------------------
  * Replaces VertexScalarField.minimiser / proc_minimisers (reference _vertex.py:144-151,
  * 422-426): is_min[r] = 1 iff row row0+r is non-empty and f[row0+r] < f[w] (strict) for every

@@ -1,0 +1,161 @@
+"""``shgo_b200.shgo`` / ``SHGO``: the reference's public API on the device complex.
+
+Nothing of the reference's driver is re-implemented: its ``SHGO`` class (option parsing, stopping
+criteria, iteration loop, scipy local minimisation, result assembly -- shgo/_shgo.py:490-1399) is
+used as is, from whichever driver package is importable (the reference package ``shgo`` if present,
+else scipy's vendored copy ``scipy.optimize._shgo``, a near-identical file).  What changes is the
+object behind ``SHGO.HC``: the driver module binds ``Complex`` by name at import
+(shgo/_shgo.py:17), so :func:`install` rebinds that name to :class:`DeviceComplex`; with
+``sampling_method='sobol'`` the points additionally come from the device generator through the
+driver's official custom-sampling seam (``sampling_method`` callable f(n, d), _shgo.py:226-228,
+1434-1444), bit-identical to scipy's engine.
+
+    from shgo_b200 import shgo
+    res = shgo(func, bounds, constraints=cons, n=2**20, iters=1, sampling_method='sobol')
+"""
+import contextlib
+import importlib
+
+import numpy as np
+
+from . import complex as _cx
+from . import hotpath as hp
+
+_DRIVERS = ("shgo._shgo", "scipy.optimize._shgo")
+_COMPLEX_MODULES = {"shgo._shgo": "shgo._shgo_lib._complex",
+                    "scipy.optimize._shgo": "scipy.optimize._shgo_lib._complex"}
+
+
+def driver_module(name=None):
+    """The host driver module whose SHGO class is used (first importable of `_DRIVERS`)."""
+    last = None
+    for mod in ((name,) if name else _DRIVERS):
+        try:
+            return importlib.import_module(mod)
+        except ImportError as e:  # pragma: no cover
+            last = e
+    raise ImportError("no SHGO driver found (tried %s): %s" % (", ".join(_DRIVERS), last))
+
+
+def install(driver=None):
+    """Rebind ``Complex`` in the driver module to DeviceComplex (what INTEGRATION.md asks a
+    reference maintainer to do in one line).  Returns the driver module."""
+    m = driver_module(driver)
+    cm = importlib.import_module(_COMPLEX_MODULES[m.__name__])
+    _cx._ORIGINAL_COMPLEX.setdefault(cm.__name__, cm.Complex)
+    if m.Complex is not _cx.DeviceComplex:
+        m._shgo_b200_saved_complex = m.Complex
+        m.Complex = _cx.DeviceComplex
+    _cx.DeviceComplex.scipy_constraint_rule = m.__name__.startswith("scipy.")
+    return m
+
+
+def uninstall(driver=None):
+    m = driver_module(driver)
+    saved = getattr(m, "_shgo_b200_saved_complex", None)
+    if saved is not None:
+        m.Complex = saved
+        del m._shgo_b200_saved_complex
+    return m
+
+
+@contextlib.contextmanager
+def _installed(driver=None):
+    m = driver_module(driver)
+    already = m.Complex is _cx.DeviceComplex
+    install(driver)
+    try:
+        yield m
+    finally:
+        if not already:
+            uninstall(driver)
+
+
+class DeviceSobolSampler:
+    """``sampling_method`` callable f(n, d) backed by the device generator.
+
+    Mirrors the reference's engine semantics (qmc.Sobol(d, scramble=False, seed=0), _shgo.py:703-711):
+    the state persists across calls, every call returns the NEXT n points of the sequence in [0,1)^d
+    (the driver scales them to the bounds itself, _shgo.py:1446-1449).  The scaled points of indices
+    [0, total) are also what DeviceComplex regenerates inside the fused evaluate kernel."""
+
+    def __init__(self, dim, bounds, device=None):
+        self.dim = dim
+        self.unit = hp.SobolTables([(0.0, 1.0)] * dim, device)
+        self.tab = hp.SobolTables(bounds, device)
+        self.total = 0
+        self.host = None          # scaled points [0, total) as the driver will see them
+
+    def __call__(self, n, d):
+        assert d == self.dim
+        u = hp.sobol_points(self.unit, self.total, n, "aos").cpu().numpy()
+        if self.total == 0:
+            self.host = hp.sobol_points(self.tab, 0, n, "aos").cpu().numpy()
+        else:
+            self.host = None      # several draws: the complex uploads the points it is given
+        self.total += n
+        return u
+
+
+def _make(driver_mod, func, bounds, args, constraints, n, iters, callback, minimizer_kwargs, options,
+          sampling_method, workers):
+    sampler = None
+    if sampling_method == "sobol":
+        # the driver rounds n up to a power of two for its own Sobol engine (_shgo.py:696-697);
+        # a callable sampler bypasses that, so do it here
+        nn = 100 if n is None else n
+        n = int(2 ** np.ceil(np.log2(nn)))
+        b = np.array(bounds, float) if not hasattr(bounds, "lb") else np.stack([bounds.lb, bounds.ub], 1)
+        b = b.copy()
+        b[~np.isfinite(b[:, 0]), 0] = -1e50
+        b[~np.isfinite(b[:, 1]), 1] = 1e50
+        sampler = DeviceSobolSampler(b.shape[0], b)
+        sampling_method = sampler
+    s = driver_mod.SHGO(func, bounds, args=args, constraints=constraints, n=n, iters=iters,
+                        callback=callback, minimizer_kwargs=minimizer_kwargs, options=options,
+                        sampling_method=sampling_method, workers=workers)
+    if sampler is not None:
+        s.HC._sampler = sampler
+        s.sampling_method = "sobol"       # only read by minimize() to pick the local-bounds rule
+    return s
+
+
+def SHGO(func, bounds, args=(), constraints=None, n=None, iters=None, callback=None,
+         minimizer_kwargs=None, options=None, sampling_method="simplicial", workers=1, driver=None):
+    """The driver's SHGO object (same constructor as shgo/_shgo.py:491) with ``HC`` on the device.
+    Use it like the reference's: ``s.iterate_all()``, ``s.iterate()``, ``s.res`` ..."""
+    m = install(driver)
+    return _make(m, func, bounds, args, constraints, n, iters, callback, minimizer_kwargs, options,
+                 sampling_method, workers)
+
+
+def shgo(func, bounds, args=(), constraints=None, n=100, iters=1, callback=None,
+         minimizer_kwargs=None, options=None, sampling_method="simplicial", *, workers=1, driver=None):
+    """Drop-in for the reference's ``shgo()`` (shgo/_shgo.py:22-487): same arguments, same
+    OptimizeResult fields.  The body below is the reference's own epilogue (_shgo.py:447-487)."""
+    with _installed(driver) as m:
+        if hasattr(bounds, "lb") and hasattr(bounds, "ub"):      # scipy.optimize.Bounds
+            bounds = np.stack([np.asarray(bounds.lb, float), np.asarray(bounds.ub, float)], 1).tolist()
+        s = _make(m, func, bounds, args, constraints, n, iters, callback, minimizer_kwargs, options,
+                  sampling_method, workers)
+        s.iterate_all()
+        if not s.break_routine:
+            if s.disp:
+                import logging
+                logging.info("Successfully completed construction of complex.")
+        if len(s.LMC.xl_maps) == 0:
+            # no minimiser found: report the lowest sampled vertex (_shgo.py:466-476)
+            s.find_lowest_vertex()
+            s.break_routine = True
+            s.fail_routine(mes="Failed to find a feasible minimizer point. "
+                               f"Lowest sampling point = {s.f_lowest}")
+            s.res.fun = s.f_lowest
+            s.res.x = s.x_lowest
+            s.res.nfev = s.fn
+            s.res.tnev = s.n_sampled
+        else:
+            pass
+        if not s.break_routine:
+            s.res.message = "Optimization terminated successfully."
+            s.res.success = True
+        return s.res

@@ -1,0 +1,685 @@
+"""DeviceComplex -- the CUDA-backed replacement for the reference's ``Complex`` at the ``SHGO.HC`` seam.
+
+The reference constructs ``self.HC = Complex(dim, domain, sfield, sfield_args, symmetry, constraints,
+workers)`` in exactly one place (shgo/_shgo.py:680-684) and afterwards touches only a small duck-typed
+surface:
+
+    HC.refine(n) / HC.refine_all()            grow the hypercube complex        (_shgo.py:1016,1019)
+    HC.vf_to_vv(points, simplices)            ingest qhull's vertex-face mesh   (_shgo.py:1090)
+    HC.V.process_pools()                      evaluate g, f; classify           (_shgo.py:1044,1099)
+    HC.V.nfev, HC.V.size()                                                      (_shgo.py:834,1017)
+    HC.V.cache (ordered mapping coordinate tuple -> vertex), HC.V[x]            (_shgo.py:867,1029,1115)
+    vertex .x .x_a .f .nn .minimiser() .star()                                  (_shgo.py:868,1030,1124,1264)
+
+DeviceComplex offers that surface and keeps everything that scales with the number of sample points
+on the GPU: coordinates, f, feasibility, adjacency (explicit CSR or the implicit lattice rule), the
+star test, pool compaction and the arg-min.  Python vertex objects are materialised only for what
+the driver actually looks at: the minimiser pool, the arg-min vertex and, on demand, their stars.
+
+Graph sources
+    'lattice'    whole generations of the simplicial complex (refine_all, or refine(2^d+1) from
+                 scratch): closed form, vertices generated on the device, adjacency implicit.
+    'mesh'       Sobol / custom sampling: qhull's simplices (host) -> device CSR (first-three-slot
+                 edges, exactly what Complex.vf_to_vv builds, _complex.py:1053-1074).
+    'hostgraph'  partial generations (refine(n) stopping mid-generator, _complex.py:474-512) and
+                 `symmetry`: sequential by construction, no closed form.  The
+                 driver-side Python ``Complex`` is run field-less as a pure graph generator, like
+                 qhull for the Sobol path; its vertices/edges are uploaded as points + CSR and
+                 evaluated / classified on the device like a mesh.
+
+Objective evaluation
+    registered functor (shgo_b200.functors, scipy.optimize.rosen)  -> fused device kernels
+    callable marked with @torch_vectorized                         -> called once on the (d, n) CUDA
+                                                                      tensor of coordinates
+    any other Python callable                                      -> it is user code: called per
+                                                                      vertex on the host exactly like
+                                                                      VertexCacheField.compute_sfield
+                                                                      (_vertex.py:338-352); the values
+                                                                      are uploaded and everything else
+                                                                      (mask, star test, pool) stays on
+                                                                      the device.
+There is no CPU implementation of the classification: without the CUDA library these classes raise.
+"""
+import collections
+import importlib
+
+import numpy as np
+import torch
+
+from . import functors as F
+from . import hotpath as hp
+from . import lattice as lat
+
+
+def torch_vectorized(fn):
+    """Mark an objective / constraint as torch-vectorised: fn(X, *args) with X a (d, n) float64
+    CUDA tensor (X[i] is the i-th coordinate of every point) returning an (n,) tensor."""
+    fn.shgo_b200_torch = True
+    return fn
+
+
+def _is_torch_vectorized(fn):
+    return bool(getattr(F._unwrap(fn), "shgo_b200_torch", False))
+
+
+def _split_wrapper(fn):
+    """(callable, args) of a possibly _FunctionWrapper-wrapped objective."""
+    inner = getattr(fn, "f", None)
+    if inner is not None and callable(inner) and hasattr(fn, "args"):
+        return inner, tuple(fn.args or ())
+    return fn, ()
+
+
+class DeviceVertex:
+    """Host-side handle of one vertex (the reference's VertexScalarField, _vertex.py:75-163)."""
+
+    __slots__ = ("x", "x_a", "f", "index", "feasible", "_cache", "_is_min", "__weakref__")
+
+    def __init__(self, cache, index, x_a, f, is_min, feasible=True):
+        self._cache = cache
+        self.index = int(index)
+        self.x_a = np.array(x_a, dtype=np.float64)
+        self.x = tuple(self.x_a.tolist())
+        self.f = float(f)
+        self._is_min = bool(is_min)
+        self.feasible = bool(feasible)
+
+    def __hash__(self):
+        return hash(self.x)
+
+    def __eq__(self, other):
+        return self is other
+
+    def __repr__(self):
+        return "DeviceVertex(%d, x=%r, f=%r)" % (self.index, self.x, self.f)
+
+    @property
+    def nn(self):
+        """Neighbour vertices, materialised on demand (a set, like the reference's).  Between a
+        refinement and the next process_pools() the device arrays are being rebuilt and the set is
+        empty; the only reader in that window is the dead `v_near` computation of
+        SHGO.iterate_hypercube (_shgo.py:1027-1032, its consumer is commented out)."""
+        return self._cache._neighbours(self)
+
+    def minimiser(self):
+        return self._is_min
+
+    def maximiser(self):  # unused by shgo(); kept for interface parity (_vertex.py:153-162)
+        return all(self.f > v.f for v in self.nn)
+
+    def star(self):
+        """st(v) = nn + {v}.  In the reference this INSERTS v into its own nn (_vertex.py:57-72),
+        which makes it fail the strict star test at its next re-classification; the cache
+        records that."""
+        self._cache._mark_started(self)
+        st = set(self.nn)
+        st.add(self)
+        return st
+
+    def connect(self, v):
+        raise NotImplementedError("the device complex is not edited edge by edge")
+
+    disconnect = connect
+
+
+class _NoPool:
+    """Stands in for VertexCacheField._mapwrapper (scipy._lib._util.MapWrapper): the driver only
+    ever calls its __exit__ (shgo/_shgo.py:801-802; unconditionally in scipy's copy).  `workers`
+    parallelises per-vertex Python calls in the reference; batched device evaluation replaces it."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return None
+
+    def close(self):
+        pass
+
+    terminate = join = close
+
+
+class DeviceVertexCache:
+    """The ``HC.V`` object: ordered, lazily materialised view of the device-resident vertices."""
+
+    def __init__(self, complex_):
+        self._c = complex_
+        self._mapwrapper = _NoPool()
+        self.cache = collections.OrderedDict()   # coordinate tuple -> DeviceVertex (materialised)
+        self._by_index = {}
+        self.nfev = 0
+        self._started = set()                    # coordinates on which star() was called
+        self._excluded = set()                   # started vertices re-classified since (never minima)
+        self._persistent = {}                    # coordinate tuple -> last handle of pool members
+        self._unlisted = {}                      # materialised stars (not part of `cache`)
+
+    # -- reference interface ---------------------------------------------------------------
+    def __iter__(self):
+        return iter(list(self.cache.values()))
+
+    def __getitem__(self, x):
+        x = tuple(float(v) for v in x)
+        try:
+            return self.cache[x]
+        except KeyError:
+            pass
+        if x in self._unlisted:
+            return self._unlisted[x]
+        if self._c._dirty:
+            # graph rebuilt, f not yet recomputed: hand out the handle from the last classification
+            v = self._persistent.get(x)
+            if v is None:
+                v = DeviceVertex(self, -1, x, float("nan"), False)
+                self._persistent[x] = v
+            return v
+        v = self._c._materialise_by_coordinate(x)
+        if v is None:
+            raise KeyError(
+                "%r is not a vertex of the device complex (inserting free-standing vertices is "
+                "not supported)" % (x,))
+        return v
+
+    def size(self):
+        return self._c._size()
+
+    def process_pools(self):
+        self._c._process()
+
+    # -- internals -------------------------------------------------------------------------------
+    def _reset_view(self):
+        self.cache = collections.OrderedDict()
+        self._unlisted = {}
+        self._by_index = {}
+
+    def _add(self, index, x_a, f, is_min, feasible=True, listed=True):
+        """`listed` vertices appear in `cache` (what the driver iterates: pool + arg-min); stars
+        materialised later on demand are reachable through V[x] and .nn only, so that reading
+        v.nn inside the driver's `for x in HC.V.cache` loop (disp=True, _shgo.py:1136-1139) does not
+        mutate the mapping being iterated."""
+        index = int(index)
+        v = self._by_index.get(index)
+        if v is None:
+            v = DeviceVertex(self, index, x_a, f, is_min, feasible)
+            self._by_index[index] = v
+            if listed:
+                self.cache[v.x] = v
+            else:
+                self._unlisted[v.x] = v
+            if is_min:
+                self._persistent[v.x] = v
+        return v
+
+    def _neighbours(self, v):
+        if self._c._dirty or v.index < 0 or self._by_index.get(v.index) is not v:
+            return set()
+        ids = self._c._neighbour_ids(v.index)
+        out = set()
+        missing = [i for i in ids.tolist() if i not in self._by_index]
+        if missing:
+            self._c._materialise(np.asarray(missing, np.int64), listed=False)
+        for i in ids.tolist():
+            out.add(self._by_index[i])
+        return out
+
+    def _mark_started(self, v):
+        self._started.add(self._c._stable_key(v))
+
+
+class DeviceComplex:
+    """Drop-in for ``shgo._shgo_lib._complex.Complex`` (constructor signature _complex.py:116-117)."""
+
+    scipy_constraint_rule = False
+
+    def __init__(self, dim, domain=None, sfield=None, sfield_args=(), symmetry=None,
+                 constraints=None, workers=1):
+        hp._require_cuda()
+        self.dim = int(dim)
+        self.domain = domain
+        self.bounds = [(0.0, 1.0)] * self.dim if domain is None else [tuple(map(float, b)) for b in domain]
+        self.symmetry = symmetry
+        self.sfield = sfield
+        self.sfield_args = tuple(sfield_args or ())
+        self.workers = workers
+        # `ineq` constraints only, like Complex.__init__ (_complex.py:136-152)
+        self.min_cons = constraints
+        self.g_cons, self.g_args = None, None
+        if constraints is not None:
+            cons = constraints if isinstance(constraints, (tuple, list)) else (constraints,)
+            gs, ga = [], []
+            for c in cons:
+                # reference: cons['type'] == 'ineq' (_complex.py:144); scipy's vendored copy of the
+                # driver tests `cons['type'] in ('ineq')`, a substring test that also admits 'eq' --
+                # mirrored when that driver is the one being served (set by api.install)
+                if c["type"] == "ineq" or (self.scipy_constraint_rule and c["type"] in ("ineq")):
+                    gs.append(c["fun"])
+                    ga.append(tuple(c.get("args", ())))
+            self.g_cons, self.g_args = tuple(gs), tuple(ga)
+        self.device = hp._dev()
+        self.V = DeviceVertexCache(self)
+        self.gen = 0
+        self.mode = None            # 'lattice' | 'mesh' | 'hostgraph'
+        self._dirty = False
+        # evaluation route
+        self._fid = F.functor_id(sfield) if not self.sfield_args else None
+        self._gid = F.constraint_set_id(self.g_cons, self.g_args)
+        if self._fid is not None and self._gid is None:
+            self._fid = None        # objective registered but constraints are not: generic route
+        self._torch = (self._fid is None and sfield is not None and _is_torch_vectorized(sfield)
+                       and all(_is_torch_vectorized(g) for g in (self.g_cons or ())))
+        # state
+        self._lat_gen = -1
+        self._f = self._feas = self._is_min = None
+        self._points_host = None     # (n, d) for mesh / hostgraph
+        self._row_ptr = self._col = None
+        self._row_ptr_host = self._col_host = None
+        self._n = 0
+        self._host_values = {}       # host-callable route: coordinates -> (f, feasible)
+        self._rank = None            # mesh: insertion rank of every vertex in the reference's cache
+        self._mesh_calls = 0
+        self._sampler = None
+        self._ref = None             # driver-side Python Complex used as a graph generator
+        self._ref_keys = []
+        self.argmin_index = -1
+        self.pool_indices = np.zeros(0, np.int64)
+
+    # =====================================================================================
+    # graph construction entry points (what SHGO.iterate_hypercube / iterate_delaunay call)
+    # =====================================================================================
+    def refine_all(self, centroids=True):
+        """One whole generation (Complex.refine_all / triangulate, _complex.py:514-533,359)."""
+        if self.mode in (None, "lattice") and self.symmetry is None:
+            self._enter_lattice(self._lat_gen + 1)
+        else:
+            self._ensure_hostgraph()
+            self._ref.refine_all()
+            self._sync_hostgraph()
+
+    def refine(self, n=1):
+        """Add ~n vertices (Complex.refine, _complex.py:474-512).  Completing generation 0 from
+        scratch is closed form; anything that stops mid-generator has none and is replayed on the
+        driver-side Python generator (graph only), then evaluated / classified on the device."""
+        if n is None:
+            return self.refine_all()
+        if self.mode is None and self.symmetry is None and n == 2 ** self.dim + 1:
+            return self._enter_lattice(0)
+        self._ensure_hostgraph()
+        self._ref.refine(n)
+        self._sync_hostgraph()
+
+    def vf_to_vv(self, vertices, simplices):
+        """Vertex-face mesh -> vertex-vertex graph on the device (Complex.vf_to_vv,
+        _complex.py:1053-1074): first-three-slot edges of every simplex, union with the edges of
+        earlier calls (the reference's connect() only ever adds)."""
+        if self.mode not in (None, "mesh"):
+            raise RuntimeError("vf_to_vv on a complex that was grown by refine()")
+        self.mode = "mesh"
+        pts = np.ascontiguousarray(vertices, dtype=np.float64)
+        if pts.ndim == 1:
+            pts = pts.reshape(-1, self.dim)
+        simp = np.ascontiguousarray(simplices)
+        if simp.ndim != 2 or simp.shape[0] == 0:
+            simp = np.zeros((0, 2), np.int32)
+        n = pts.shape[0]
+        simp = simp.astype(np.int32, copy=False)
+        # vertices are keyed by coordinate tuple in the reference: coincident points are ONE vertex
+        canon = self._coincident_map(pts)
+        if canon is not None:
+            simp = canon[simp].astype(np.int32)
+        simp_d = torch.from_numpy(np.ascontiguousarray(simp)).to(self.device)
+        # insertion order of the reference's vertex cache = order of first appearance while
+        # vf_to_vv walks the simplices; vertices of earlier calls keep their (earlier) rank
+        fs = hp.first_seen(simp_d, n)
+        rank = torch.where(fs >= 0, fs + (self._mesh_calls << 44), torch.full_like(fs, 2 ** 62))
+        if self._rank is not None:
+            old = torch.full_like(rank, 2 ** 62)
+            old[: self._rank.numel()] = self._rank
+            rank = torch.minimum(old, rank)
+        self._rank = rank
+        self._mesh_calls += 1
+        if self._row_ptr is not None and self._n > 0:
+            # carry the edges of earlier triangulations over as degenerate [a, b, b] triples
+            rp, col = self._row_ptr, self._col
+            rows = torch.repeat_interleave(torch.arange(self._n, device=self.device, dtype=torch.int32),
+                                           (rp[1:] - rp[:-1]).to(torch.int64))
+            keep = rows < col
+            old = torch.stack([rows[keep], col[keep], col[keep]], 1)
+            new = simp_d[:, :3] if simp_d.shape[1] >= 3 else torch.cat([simp_d, simp_d[:, 1:2]], 1)
+            simp_d = torch.cat([old, new.to(torch.int32)], 0).contiguous()
+        self._row_ptr, self._col = hp.csr_from_simplices(simp_d, n)
+        self._row_ptr_host = self._col_host = None
+        self._points_host = pts
+        self._n = n
+        self._dirty = True
+
+    # =====================================================================================
+    # evaluation + classification  (VertexCacheField.process_pools, _vertex.py:324-328)
+    # =====================================================================================
+    def _process(self):
+        if self.mode is None or not self._dirty:
+            return
+        if self.mode == "lattice":
+            self._process_lattice()
+        else:
+            self._process_explicit()
+        self._dirty = False
+
+    # ---- lattice ---------------------------------------------------------------------------
+    def _enter_lattice(self, gen):
+        self.mode = "lattice"
+        self._tab_host = lat.coordinate_tables(self.bounds, gen)   # raises on fp64 artefact bounds
+        self._tab = torch.from_numpy(self._tab_host).to(self.device)
+        self._lat_gen = gen
+        self.gen = gen
+        self._n, self._ngrid = lat.counts(self.dim, gen)
+        if self._n >= 2 ** 32:
+            raise MemoryError("generation %d of a %d-D lattice has %d vertices" % (gen, self.dim, self._n))
+        self._dirty = True
+
+    def _process_lattice(self):
+        d, gen, n = self.dim, self._lat_gen, self._n
+        if self._fid is not None:
+            self._f, self._feas = hp.lattice_eval(self._fid, self._gid, d, gen, self._tab, 0, n)
+        elif self._torch:
+            x = hp.lattice_coords(d, gen, self._tab, 0, n)
+            self._f, self._feas = self._evaluate_generic(x, None)
+        else:
+            pts = self._coordinates(np.arange(n, dtype=np.int64))
+            self._f, self._feas = self._evaluate_generic(None, pts)
+        self._is_min = hp.lattice_star(d, gen, self._f)
+        self.V.nfev = int(self._feas.sum().item())
+        self._finish_classification(present=None)
+
+    # ---- explicit graphs (mesh, hostgraph) -------------------------------------------------
+    def _process_explicit(self):
+        n = self._n
+        if n == 0:
+            return
+        pts = self._points_host
+        if self._fid is not None:
+            tab = self._sampler_tables_if_points_are_sobol(pts)
+            if tab is not None:
+                self._f, self._feas = hp.eval_sobol(self._fid, self._gid, tab, 0, n)
+            else:
+                x = torch.from_numpy(pts).to(self.device).t().contiguous()
+                self._f, self._feas = hp.eval_points(self._fid, self._gid, x)
+        elif self._torch:
+            x = torch.from_numpy(pts).to(self.device).t().contiguous()
+            self._f, self._feas = self._evaluate_generic(x, None)
+        else:
+            self._f, self._feas = self._evaluate_generic(None, pts)
+        nf = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._is_min = hp.star_csr(self._row_ptr, self._col, self._f, feasible=self._feas, nfev=nf)
+        self.V.nfev = int(nf.item())
+        present = (self._row_ptr[1:] > self._row_ptr[:-1]).to(torch.uint8)
+        if self.mode == "hostgraph":
+            # every vertex the generator created exists, also one without edges yet: it is
+            # trivially a minimiser (all([]) is True, _vertex.py:148) and counts towards nfev;
+            # in a mesh a point without edges is NOT a vertex
+            self._is_min = torch.where(present.bool(), self._is_min, torch.ones_like(self._is_min))
+            self.V.nfev = int(self._feas.sum().item())
+            present = None
+        self._finish_classification(present)
+        if self.mode == "hostgraph":
+            for v in self._ref.V.cache.values():   # "classified": edge changes from here on count
+                v.check_min = False
+
+    def _evaluate_generic(self, x_soa, pts_host):
+        """torch-vectorised or host-callable objective + constraints; returns device (f, feasible)."""
+        n = self._n
+        func, fargs = _split_wrapper(self.sfield)
+        fargs = fargs + self.sfield_args
+        if x_soa is not None:
+            g = None
+            if self.g_cons:
+                g = torch.stack([torch.as_tensor(gc(x_soa, *ga), dtype=torch.float64, device=self.device)
+                                 .expand(n).contiguous() for gc, ga in zip(self.g_cons, self.g_args)])
+            f = torch.as_tensor(func(x_soa, *fargs), dtype=torch.float64, device=self.device)
+            f = f.expand(n).contiguous().clone()
+            return hp.mask_infeasible(f, g)
+        # user Python code: called per vertex, once per vertex that exists (results are cached by
+        # coordinates like the reference's vertex cache), with the reference's semantics
+        # (feasibility_check / compute_sfield, _vertex.py:330-352)
+        if self.mode in ("lattice", "hostgraph"):
+            present = np.arange(n)
+        else:
+            rp = self._row_ptr_cpu()
+            present = np.flatnonzero(rp[1:] > rp[:-1])
+        f_host = np.full(n, np.inf)
+        feas_host = np.ones(n, np.uint8)
+        known = self._host_values
+        for i in present.tolist():
+            xa = pts_host[i]
+            key = xa.tobytes()
+            hit = known.get(key)
+            if hit is None:
+                ok = True
+                if self.g_cons:
+                    for gc, ga in zip(self.g_cons, self.g_args):
+                        # scalar g: the reference's `g(x) < 0.0`; scipy's copy of the driver also
+                        # admits vector-valued constraints (`np.any(g(x) < 0)`)
+                        if np.any(np.asarray(gc(xa, *ga)) < 0.0):
+                            ok = False
+                            break
+                v = np.inf
+                if ok:
+                    try:
+                        v = float(np.squeeze(func(xa, *fargs)))
+                    except AttributeError:
+                        v = np.inf
+                    if np.isnan(v):
+                        v = np.inf
+                hit = known[key] = (v, ok)
+            f_host[i] = hit[0]
+            feas_host[i] = 1 if hit[1] else 0
+        return (torch.from_numpy(f_host).to(self.device), torch.from_numpy(feas_host).to(self.device))
+
+    def _row_ptr_cpu(self):
+        if self._row_ptr_host is None:
+            self._row_ptr_host = self._row_ptr.cpu().numpy()
+        return self._row_ptr_host
+
+    def _col_cpu(self):
+        if self._col_host is None:
+            self._col_host = self._col.cpu().numpy()
+        return self._col_host
+
+    # ---- shared tail: pool, arg-min, materialisation of what the driver will look at ----------
+    def _finish_classification(self, present):
+        V = self.V
+        idx, cnt = hp.compact_pool(self._is_min)
+        pool = idx[: int(cnt.item())].cpu().numpy()
+        # the star() self-loop quirk: a vertex that was a local-search start is
+        # never a minimiser again once it has been re-classified after an edge change
+        if V._started:
+            V._excluded |= self._started_and_changed()
+            if V._excluded:
+                keys = self._stable_keys_of(pool)
+                pool = pool[np.array([k not in V._excluded for k in keys], bool)] if len(pool) else pool
+        self.pool_indices = pool
+        self.argmin_index, self.argmin_value = hp.argmin(self._f, present)
+        V._reset_view()
+        want = pool
+        if self.argmin_index >= 0:
+            want = np.union1d(pool, [self.argmin_index])
+        want = np.asarray(want, np.int64)
+        if self.mode == "mesh" and self._rank is not None and len(want) > 1:
+            # list the vertices in the reference's cache order: SHGO.minimizers builds X_min in
+            # that order and minimise_pool starts from X_min[0] (_shgo.py:1146-1152,1177)
+            r = self._rank[torch.from_numpy(want).to(self.device)].cpu().numpy()
+            want = want[np.argsort(r, kind="stable")]
+        self._materialise(want, pool_set=set(pool.tolist()))
+
+    def _materialise(self, ids, pool_set=None, listed=True):
+        if len(ids) == 0:
+            return
+        ids = np.asarray(ids, np.int64)
+        t = torch.from_numpy(ids).to(self.device)
+        f = self._f[t].cpu().numpy()
+        feas = self._feas[t].cpu().numpy() if self._feas is not None else np.ones(len(ids), np.uint8)
+        x = self._coordinates(ids)
+        if pool_set is None:
+            pool_set = set(self.pool_indices.tolist())
+        for i, xi, fi, fe in zip(ids.tolist(), x, f, feas):
+            self.V._add(i, xi, fi, i in pool_set, bool(fe), listed)
+
+    def _coordinates(self, ids):
+        if self.mode == "lattice":
+            p = lat.decode(ids, self.dim, self._lat_gen)
+            return np.stack([self._tab_host[i][p[:, i]] for i in range(self.dim)], 1)
+        return self._points_host[ids]
+
+    def _materialise_by_coordinate(self, x):
+        if self.mode == "lattice":
+            p = []
+            for i, xi in enumerate(x):
+                hit = np.flatnonzero(self._tab_host[i] == xi)
+                if len(hit) == 0:
+                    return None
+                p.append(int(hit[0]))
+            par = {q & 1 for q in p}
+            if len(par) != 1:
+                return None
+            if par == {0}:
+                vid = int(lat.vertex_ids(np.array([[q // 2 for q in p]]), self.dim, self._lat_gen, True)[0])
+            else:
+                vid = int(lat.vertex_ids(np.array([[q // 2 for q in p]]), self.dim, self._lat_gen, False)[0])
+        elif self._points_host is not None:
+            hit = np.flatnonzero(np.all(self._points_host == np.asarray(x), axis=1))
+            if len(hit) == 0:
+                return None
+            vid = int(hit[0])
+        else:
+            return None
+        if self._f is None:
+            return None
+        self._materialise(np.array([vid], np.int64), listed=False)
+        return self.V._by_index.get(vid)
+
+    def _neighbour_ids(self, index):
+        if self.mode == "lattice":
+            return lat.neighbours(index, self.dim, self._lat_gen)
+        rp, col = self._row_ptr_cpu(), self._col_cpu()
+        return col[rp[index]:rp[index + 1]].astype(np.int64)
+
+    def _size(self):
+        if self.mode is None:
+            return 0
+        if self.mode == "lattice":
+            return self._n
+        if self.mode == "hostgraph":
+            return self._n
+        rp = self._row_ptr_cpu()
+        return int(np.count_nonzero(rp[1:] > rp[:-1]))
+
+    # ---- star() bookkeeping -----------------------------------------------------------------
+    def _stable_key(self, v):
+        """identity of a vertex across generations / iterations: its coordinates"""
+        return v.x
+
+    def _stable_keys_of(self, ids):
+        return [tuple(c) for c in self._coordinates(np.asarray(ids, np.int64)).tolist()]
+
+    def _started_and_changed(self):
+        if self.mode == "hostgraph":
+            changed = set()
+            for key in self.V._started:
+                rv = self._ref.V.cache.get(key)
+                if rv is not None and getattr(rv, "check_min", True):
+                    changed.add(key)
+            return changed
+        # whole-generation refinement and re-triangulation re-classify every vertex
+        return set(self.V._started) if self.mode == "lattice" else set()
+
+    # ---- hostgraph ----------------------------------------------------------------------------
+    def _ensure_hostgraph(self):
+        if self.mode == "hostgraph":
+            return
+        if self.mode == "mesh":
+            raise RuntimeError("refine() on a complex that was built from a mesh")
+        RefComplex = _driver_complex_class()
+        # field-less in effect: the dummy field is never evaluated (process_pools is never called
+        # on it); it only makes the generator create vertices that carry check_min flags
+        self._ref = RefComplex(self.dim, domain=self.bounds, sfield=_never_called, symmetry=self.symmetry)
+        if self.mode == "lattice":
+            # replay the whole generations already built, then continue step-wise
+            self._ref.refine(None)
+            for _ in range(self._lat_gen):
+                self._ref.refine_all()
+            for v in self._ref.V.cache.values():
+                v.check_min = False
+        self.mode = "hostgraph"
+        self._ref_keys = []
+
+    def _sync_hostgraph(self):
+        """vertices / edges of the Python generator -> points + CSR on the device"""
+        cache = self._ref.V.cache
+        keys = list(cache.keys())
+        assert keys[:len(self._ref_keys)] == self._ref_keys  # insertion order is append-only
+        self._ref_keys = keys
+        n = len(keys)
+        index = {k: i for i, k in enumerate(keys)}
+        deg = np.fromiter((len(v.nn) for v in cache.values()), np.int64, n)
+        rp = np.zeros(n + 1, np.int64)
+        np.cumsum(deg, out=rp[1:])
+        col = np.empty(max(int(rp[-1]), 1), np.int32)
+        for i, v in enumerate(cache.values()):
+            if deg[i]:
+                col[rp[i]:rp[i + 1]] = sorted(index[w.x] for w in v.nn)
+        col = col[: int(rp[-1])]
+        self._points_host = np.array(keys, np.float64).reshape(n, self.dim)
+        self._row_ptr_host, self._col_host = rp, col
+        self._row_ptr = torch.from_numpy(rp).to(self.device)
+        colp = np.zeros(max(len(col), 4), np.int32)
+        colp[:len(col)] = col
+        self._col = torch.from_numpy(colp).to(self.device)[:len(col)]
+        self._n = n
+        self._dirty = True
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def _coincident_map(self, pts):
+        """canonical index of every point (first occurrence of its coordinates), or None when all
+        points are distinct"""
+        n = pts.shape[0]
+        if n < 2:
+            return None
+        order = np.lexsort(pts.T[::-1])
+        sp = pts[order]
+        same = np.all(sp[1:] == sp[:-1], axis=1)
+        if not same.any():
+            return None
+        grp = np.concatenate([[0], np.cumsum(~same)])
+        first = np.full(grp[-1] + 1, n, np.int64)
+        np.minimum.at(first, grp, order)
+        canon = np.empty(n, np.int64)
+        canon[order] = first[grp]
+        return canon
+
+    def _sampler_tables_if_points_are_sobol(self, pts):
+        """The fused generate->evaluate kernel applies when the mesh's points are exactly Sobol
+        indices [0, n) of the registered device sampler (checked on a few rows)."""
+        s = self._sampler
+        if s is None or s.total != pts.shape[0] or s.host is None:
+            return None
+        probe = np.unique(np.clip(np.array([0, 1, pts.shape[0] // 2, pts.shape[0] - 1]), 0, pts.shape[0] - 1))
+        if not np.array_equal(pts[probe], s.host[probe]):
+            return None
+        return s.tab
+
+
+def _never_called(x, *args):  # pragma: no cover
+    raise RuntimeError("the graph generator must not evaluate the objective")
+
+
+def _driver_complex_class():
+    """The Python Complex of whichever driver package is importable (the reference `shgo`, else
+    scipy's vendored copy); used ONLY as a sequential graph generator for partial generations."""
+    for mod in ("shgo._shgo_lib._complex", "scipy.optimize._shgo_lib._complex"):
+        try:
+            m = importlib.import_module(mod)
+            return _ORIGINAL_COMPLEX.get(mod, m.Complex)
+        except ImportError:
+            continue
+    raise ImportError("no shgo driver package found (need `shgo` or scipy.optimize)")
+
+
+_ORIGINAL_COMPLEX = {}

@@ -332,6 +332,22 @@ __global__ void edge_insert_kernel(const int32_t *__restrict__ simplices, uint64
     }
 }
 
+// order in which Complex.vf_to_vv first touches each vertex (simplex by simplex, slots 0,1,2):
+// the insertion order of the reference's vertex cache, which decides the order of its pool
+__global__ void first_seen_kernel(const int32_t *__restrict__ simplices, uint64_t S, int dp1, uint64_t n,
+                                  unsigned long long *__restrict__ first)
+{
+    const int nslot = dp1 >= 3 ? 3 : 2;
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < S;
+         s += (uint64_t)gridDim.x * blockDim.x) {
+        const int32_t *sp = simplices + s * (uint64_t)dp1;
+        for (int k = 0; k < nslot; ++k) {
+            const int32_t v = __ldg(sp + k);
+            if ((uint32_t)v < n) atomicMin(first + v, (unsigned long long)(s * 3 + k));
+        }
+    }
+}
+
 __global__ void edge_fill_kernel(const unsigned long long *__restrict__ table, uint64_t slots,
                                  const int64_t *__restrict__ row_ptr, uint32_t *__restrict__ cursor,
                                  int32_t *__restrict__ col_tmp)
@@ -594,6 +610,21 @@ int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, 
         edge_fill_kernel<<<grid_for(slots, 256, 8), 256, 0, st>>>(table, slots, row_ptr, cursor, col_tmp);
         row_sort_kernel<<<grid_for(n * 32, 256, 8), 256, 0, st>>>(row_ptr, n, col_tmp, col);
     }
+    SHGO_CUDA_TRY(cudaGetLastError());
+    return SHGO_B200_OK;
+}
+
+int shgo_b200_first_seen(const int32_t *simplices, uint64_t S, int dp1, uint64_t n, uint64_t *first_seen,
+                         void *stream)
+{
+    SHGO_REQUIRE(first_seen, "null output");
+    SHGO_REQUIRE(simplices || S == 0, "null simplices");
+    SHGO_REQUIRE(dp1 >= 2, "simplices need at least two vertex slots (dp1 = %d)", dp1);
+    cudaStream_t st = as_stream(stream);
+    SHGO_CUDA_TRY(cudaMemsetAsync(first_seen, 0xff, n * sizeof(uint64_t), st));
+    if (S == 0 || n == 0) return SHGO_B200_OK;
+    first_seen_kernel<<<grid_for(S, 256, 8), 256, 0, st>>>(
+        simplices, S, dp1, n, reinterpret_cast<unsigned long long *>(first_seen));
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;
 }

@@ -125,6 +125,16 @@ def csr_from_simplices(simplices, n):
     return row_ptr, col[: int(nnz.item())]
 
 
+def first_seen(simplices, n):
+    """int64 [n]: position at which vf_to_vv first touches each vertex (-1 = never)."""
+    assert simplices.dtype == torch.int32 and simplices.dim() == 2
+    simplices = simplices.contiguous()
+    out = torch.empty(n, dtype=torch.int64, device=simplices.device)
+    _lib.call("shgo_b200_first_seen", _ptr(simplices), simplices.shape[0], simplices.shape[1], n,
+              _ptr(out), _stream())
+    return out
+
+
 def star_csr(row_ptr, col, f, row0=0, rows=None, is_min=None, feasible=None, nfev=None):
     """Star test of rows [row0, row0+rows).  With `nfev` (1-element int64 tensor) the same pass
     also counts the rows that exist and are feasible (`feasible` indexed like is_min)."""

@@ -1,0 +1,116 @@
+"""TEST INFRASTRUCTURE: a CPU stand-in for shgo_b200.hotpath built on the oracle.
+
+Lets the `-m "not gpu"` suite exercise the HOST logic of DeviceComplex / the shgo() wrapper (lazy
+vertex materialisation, star() bookkeeping, mode switching, mesh unions, host-callable route) in
+a container without a GPU.  It is never imported by the product; the GPU suite runs the same tests
+against the real kernels.
+"""
+import numpy as np
+import torch
+
+from oracle import oracle as orc
+
+_FN = {v: k for k, v in orc.FUNCTOR_IDS.items()}
+_GN = {0: None, 1: "cattle_feed", 2: "sum_le_6"}
+CPU = torch.device("cpu")
+
+
+class SobolTables:
+    def __init__(self, bounds, device=None):
+        b = np.asarray(bounds, np.float64)
+        self.d = b.shape[0]
+        self.lb_host, self.ub_host = b[:, 0].copy(), b[:, 1].copy()
+        self.sv_host = orc.sobol_dirnums(self.d)
+        self.sv = torch.zeros(1)
+
+
+def sobol_points(tab, k0, n, layout="soa", out=None):
+    x = orc.sobol_points(tab.sv_host, k0, n, tab.lb_host, tab.ub_host)
+    return torch.from_numpy(x.T.copy() if layout == "soa" else x)
+
+
+def eval_sobol(functor, gset, tab, k0, n, f=None, feasible=None, want_feasible=True):
+    fo, fe = orc.sobol_eval(tab.sv_host, _FN[functor], _GN[gset], k0, n, tab.lb_host, tab.ub_host)
+    return torch.from_numpy(fo), torch.from_numpy(fe)
+
+
+def eval_points(functor, gset, x_soa, f=None, feasible=None):
+    fo, fe = orc.eval_points(_FN[functor], _GN[gset], np.ascontiguousarray(x_soa.numpy().T))
+    return torch.from_numpy(fo), torch.from_numpy(fe)
+
+
+def mask_infeasible(f, g=None, feasible=None):
+    fh = f.numpy().copy()
+    ok = np.ones(len(fh), bool)
+    if g is not None:
+        ok = ~np.any(g.numpy() < 0.0, axis=0)
+    fh[~ok | np.isnan(fh)] = np.inf
+    return torch.from_numpy(fh), torch.from_numpy(ok.astype(np.uint8))
+
+
+def csr_from_simplices(simplices, n):
+    rp, col = orc.vf_to_vv(simplices.numpy().astype(np.int32), n)
+    return torch.from_numpy(rp), torch.from_numpy(col)
+
+
+def first_seen(simplices, n):
+    s = simplices.numpy()
+    k = min(s.shape[1], 3)
+    flat = s[:, :k].reshape(-1).astype(np.int64)
+    pos = (np.arange(s.shape[0])[:, None] * 3 + np.arange(k)[None, :]).reshape(-1)
+    out = np.full(n, -1, np.int64)
+    u, first = np.unique(flat, return_index=True)
+    out[u] = pos[first]
+    return torch.from_numpy(out)
+
+
+def star_csr(row_ptr, col, f, row0=0, rows=None, is_min=None, feasible=None, nfev=None):
+    rp, c = row_ptr.numpy(), np.ascontiguousarray(col.numpy())
+    out = orc.star_csr(rp, c, f.numpy(), row0, rows)
+    if nfev is not None:
+        nfev[0] = orc.nfev(rp, None if feasible is None else feasible.numpy())
+    return torch.from_numpy(out)
+
+
+def compact_pool(is_min, base=0, cap=None, work=None):
+    idx = orc.compact_pool(np.ascontiguousarray(is_min.numpy())) + base
+    return torch.from_numpy(idx), torch.tensor(len(idx))
+
+
+def argmin(f, present=None):
+    fh = f.numpy()
+    i = orc.argmin(fh, None if present is None else np.ascontiguousarray(present.numpy()))
+    return i, (float(fh[i]) if i >= 0 else float("inf"))
+
+
+def _bounds_from_tab(tab):
+    t = tab.numpy()
+    return [(row[0], row[-1]) for row in t]
+
+
+def lattice_eval(functor, gset, d, gen, tab, v0, nv, f=None, feasible=None):
+    x = orc.lattice_coords(_bounds_from_tab(tab), gen)[v0:v0 + nv]
+    fo, fe = orc.eval_points(_FN[functor], _GN[gset], x)
+    return torch.from_numpy(fo), torch.from_numpy(fe)
+
+
+def lattice_coords(d, gen, tab, v0, nv):
+    x = orc.lattice_coords(_bounds_from_tab(tab), gen)[v0:v0 + nv]
+    return torch.from_numpy(np.ascontiguousarray(x.T))
+
+
+def lattice_star(d, gen, f, v0=0, nv=None, is_min=None):
+    out = orc.lattice_star(d, gen, f.numpy())
+    nv = len(out) - v0 if nv is None else nv
+    return torch.from_numpy(out[v0:v0 + nv].copy())
+
+
+def install(monkeypatch):
+    """Patch shgo_b200.hotpath in place (functions are looked up as attributes at call time)."""
+    from shgo_b200 import hotpath as hp
+    for name in ("SobolTables", "sobol_points", "eval_sobol", "eval_points", "mask_infeasible",
+                 "csr_from_simplices", "first_seen", "star_csr", "compact_pool", "argmin", "lattice_eval",
+                 "lattice_coords", "lattice_star"):
+        monkeypatch.setattr(hp, name, globals()[name])
+    monkeypatch.setattr(hp, "_require_cuda", lambda: None)
+    monkeypatch.setattr(hp, "_dev", lambda device=None: CPU)

@@ -1,0 +1,121 @@
+"""HOST logic of DeviceComplex and the shgo() wrapper, on CPU, with the oracle standing in for the
+kernels (tests/fake_hotpath.py).  The same scenarios run against the real kernels in
+tests/test_gpu_api.py.  Comparator: the driver with its own Python Complex, same process."""
+import numpy as np
+import pytest
+
+import fake_hotpath
+from conftest import load_golden
+
+
+@pytest.fixture()
+def sb(monkeypatch):
+    fake_hotpath.install(monkeypatch)
+    import shgo_b200
+    from shgo_b200 import api
+    yield shgo_b200
+    api.uninstall()
+
+
+def _reference_run(fn, *a, **k):
+    from shgo_b200 import api
+    m = api.driver_module()
+    assert getattr(m, "_shgo_b200_saved_complex", None) is None
+    return m.shgo(fn, *a, **k)
+
+
+def test_readme_example(sb):
+    from scipy.optimize import rosen
+    g = load_golden("end_to_end")
+    res = sb.shgo(rosen, [(0, 2)] * 5)
+    assert res.success and res.nfev == int(g["rosen5_nfev"])
+    np.testing.assert_allclose(res.x, g["rosen5_x"], atol=1e-8)
+
+
+def test_cattle_feed(sb):
+    from shgo_b200 import functors as F
+    g = load_golden("end_to_end")
+    cons = ({"type": "ineq", "fun": F.cattle_feed_g1}, {"type": "ineq", "fun": F.cattle_feed_g2},
+            {"type": "eq", "fun": F.cattle_feed_h1})
+    res = sb.shgo(F.cattle_feed, [(0, 1.0)] * 4, n=150, constraints=cons)
+    assert res.success and res.nfev == int(g["cattle_nfev"])
+    assert res.fun == pytest.approx(float(g["cattle_fun"]), rel=1e-9)
+
+
+def test_eggholder_sobol(sb):
+    from shgo_b200 import functors as F
+    g = load_golden("end_to_end")
+    res = sb.shgo(F.eggholder, [(-512, 512)] * 2, n=64, sampling_method="sobol")
+    assert len(res.funl) == len(g["egg_funl"]) and res.nfev == int(g["egg_nfev"])
+    np.testing.assert_allclose(res.funl, g["egg_funl"], rtol=1e-8)
+
+
+KW = [dict(n=None, iters=3, sampling_method="simplicial"),
+      dict(n=30, iters=3, sampling_method="simplicial"),
+      dict(n=100, iters=2, sampling_method="simplicial"),
+      dict(n=128, iters=1, sampling_method="sobol"),
+      dict(n=64, iters=3, sampling_method="sobol")]
+
+
+@pytest.mark.parametrize("kw", KW)
+@pytest.mark.parametrize("problem", ["rastrigin2", "ackley3", "sphere_cons", "python_callable"])
+def test_same_result_as_driver_with_python_complex(sb, kw, problem):
+    from shgo_b200 import functors as F
+    if problem == "rastrigin2":
+        fn, bounds, cons = F.rastrigin, [(-5.12, 5.12)] * 2, None
+    elif problem == "ackley3":
+        fn, bounds, cons = F.ackley, [(-32.768, 32.768)] * 3, None
+    elif problem == "sphere_cons":
+        fn, bounds, cons = F.sphere, [(-1, 6)] * 2, ({"type": "ineq", "fun": F.sum_le_6},)
+    else:
+        def fn(x):
+            return (x[0] - 0.3) ** 2 + np.sin(3 * x[1]) + 0.1 * x[0] * x[1]
+        bounds, cons = [(-2, 2), (-3, 1)], None
+    ref = _reference_run(fn, bounds, constraints=cons, **kw)
+    res = sb.shgo(fn, bounds, constraints=cons, **kw)
+    assert res.success == ref.success
+    assert res.nfev == ref.nfev and res.nit == ref.nit
+    assert len(res.funl) == len(ref.funl)
+    np.testing.assert_allclose(res.funl, ref.funl, rtol=1e-7, atol=1e-9)
+    # minima with exactly equal f (symmetric problems) may come out in a different order: the
+    # reference breaks such ties by the insertion order of its vertex cache (documented deviation)
+    key = lambda a: np.lexsort(np.round(np.asarray(a), 5).T[::-1])
+    np.testing.assert_allclose(np.asarray(res.xl)[key(res.xl)], np.asarray(ref.xl)[key(ref.xl)],
+                               rtol=1e-6, atol=1e-6)
+
+
+def test_pool_objects_and_lazy_cache(sb):
+    from shgo_b200 import functors as F
+    s = sb.SHGO(F.rastrigin, [(-5.12, 5.12)] * 3, n=None, iters=3)
+    s.iterate()
+    s.iterate()
+    s.iterate_complex()
+    s.minimizers()
+    V = s.HC.V
+    assert s.HC.mode == "lattice" and V.size() == 189 and V.nfev == 189
+    assert len(V.cache) < 60                         # only pool + arg-min materialised, not 189
+    for v in s.minimizer_pool:
+        assert v.minimiser() and all(v.f < w.f for w in v.nn)
+        assert V[v.x] is v and v.x_a.shape == (3,)
+
+
+def test_infeasible_and_flat_problems(sb):
+    def table(x):
+        return 0.0 if x[0] > 3.0 else 3.0
+    res = sb.shgo(table, [(-10, 10)] * 2, n=64, sampling_method="sobol")
+    ref = _reference_run(table, [(-10, 10)] * 2, n=64, sampling_method="sobol")
+    assert res.success == ref.success and res.nfev == ref.nfev
+
+    def g_bad(x):
+        return -1.0 - x[0] ** 2
+    cons = ({"type": "ineq", "fun": g_bad},)
+    res = sb.shgo(lambda x: x[0] ** 2 + x[1] ** 2, [(-1, 1)] * 2, constraints=cons, n=32,
+                  sampling_method="sobol")
+    assert not res.success and res.nfev == 0
+
+
+def test_lattice_artefact_bounds_refused(sb):
+    from shgo_b200.lattice import LatticeArtefactError
+    from shgo_b200 import functors as F
+    with pytest.raises(LatticeArtefactError):
+        sb.shgo(F.sphere, [(-3.3, 7.1)] * 3, n=None, iters=2)
