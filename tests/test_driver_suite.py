@@ -20,7 +20,8 @@ def _run(fake):
                os.environ.get("PYTHONPATH", ""))
     env["SHGO_B200_FAKE"] = "1" if fake else "0"
     r = subprocess.run([sys.executable, "-m", "pytest", t.__file__, "-q", "-x", "-p", "driver_suite_plugin",
-                        "-p", "no:cacheprovider", "-W", "ignore::DeprecationWarning"],
+                        "-p", "no:cacheprovider", "-W", "ignore::DeprecationWarning",
+                        "-W", "ignore::pytest.PytestUnknownMarkWarning"],
                        env=env, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
