@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--log2n", type=int, default=28, help="log2 of the total number of points")
     ap.add_argument("--e2e-log2n", type=int, default=26, help="log2 n of the host-buffer (e2e) leg")
     ap.add_argument("--cpu-log2n", type=int, default=24, help="log2 n of the CPU baseline sample")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
+                    help="how neighbour f values cross GPUs (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -179,6 +181,7 @@ def main():
     tab = hp.SobolTables(BOUNDS, dev)
 
     # ---- graph shard (inputs resident in HBM before the timed region) -----------------------
+    from shgo_b200 import dist as sdist
     row_ptr_l = torch.arange(row0 * m, (row0 + rows + 1) * m, m, dtype=torch.int64, device=dev)
     col_l = torch.empty((rows, m), dtype=torch.int32, device=dev)
     bits = (1 << torch.arange(m, dtype=torch.int32, device=dev))[None, :]
@@ -187,28 +190,13 @@ def main():
         i = torch.arange(row0 + s, row0 + e, dtype=torch.int32, device=dev)[:, None]
         torch.bitwise_xor(i, bits, out=col_l[s:e])
     col_l = col_l.reshape(-1)
-    # the C ABI addresses the whole graph; a shard passes the virtual base of its slices
-    rp_base = row_ptr_l.data_ptr() - row0 * 8
-    col_base = col_l.data_ptr() - row0 * m * 4
-    f_all = torch.empty(n, dtype=torch.float64, device=dev)
-    f_my = f_all[row0:row0 + rows]
-    feas = torch.empty(rows, dtype=torch.uint8, device=dev)
-    is_min = torch.empty(rows, dtype=torch.uint8, device=dev)
-    work = hp.PoolWorkspace(rows, rows // 8, dev)
-    nfev = torch.zeros(1, dtype=torch.int64, device=dev)
+    del bits, i
+    it = sdist.ShardedSobolIteration(fid, F.G_NONE, tab, n, row_ptr_l, col_l, exchange=args.exchange,
+                                     pool_cap=rows // 8)
     stream = torch.cuda.current_stream()
 
     def step(ev=None):
-        hp.eval_sobol(fid, F.G_NONE, tab, row0, rows, f=f_my, feasible=feas)
-        if world > 1:
-            dist.all_gather_into_tensor(f_all, f_my)
-        if ev:
-            ev[0].record(stream)
-        _lib.call("shgo_b200_star_csr_nfev", rp_base, col_base, f_all.data_ptr(), feas.data_ptr(), row0,
-                  rows, rows * m, is_min.data_ptr(), nfev.data_ptr(), stream.cuda_stream)
-        if ev:
-            ev[1].record(stream)
-        hp.compact_pool(is_min, base=row0, work=work)
+        it.step(ev)
 
     def barrier():
         if world > 1:
@@ -221,12 +209,12 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    # the timed region is tens of ms; keep the same load running until nvidia-smi (100 ms period,
-    # slow to start) has actually sampled it, so the clocks line describes this workload
-    t_w = time.perf_counter()
-    while rank == 0 and world == 1 and len(sampler.rows) < 3 and time.perf_counter() - t_w < 5.0:
+    # the timed region is tens of ms; keep the same load running (all ranks, fixed count) long
+    # enough for nvidia-smi (100 ms period, slow to start) to sample it, so that the clocks line
+    # describes this workload
+    for _ in range(40):
         step()
-        torch.cuda.synchronize()
+    barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -245,17 +233,17 @@ def main():
     ms_step = float(tt[0].item()) / args.steps
     star_ms = float(tt[1].item())
     value = n / (ms_step * 1e-3)
-    pool_count = int(work.count[0].item())
-    pc = torch.tensor([pool_count, int(nfev.item())], dtype=torch.int64, device=dev)
+    pc = torch.tensor([int(it.work.count[0].item()), int(it.nfev.item())], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(pc)
+    pool_cap_local = it.work.cap
 
     # eval kernel alone (for the FP64 side of the roofline)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record(stream)
     for _ in range(5):
-        hp.eval_sobol(fid, F.G_NONE, tab, row0, rows, f=f_my, feasible=feas)
+        hp.eval_sobol(fid, F.G_NONE, tab, row0, rows, f=it.f_my, feasible=it.feas)
     e1.record(stream)
     torch.cuda.synchronize()
     eval_ms = e0.elapsed_time(e1) / 5
@@ -267,6 +255,7 @@ def main():
         me = min(args.e2e_log2n, args.log2n)
         re_ = ne // world
         r0e = rank * re_
+        it.close()
         del col_l, row_ptr_l
         torch.cuda.empty_cache()
         rp_h = torch.arange(0, (re_ + 1) * me, me, dtype=torch.int64).pin_memory()
@@ -339,6 +328,7 @@ def main():
         if world == 1:
             _lib.lib().shgo_b200_ctx_destroy(ctx)
 
+    it.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,7 +348,10 @@ def main():
         "config": {"workload": workload_name(args.log2n), "points": n, "rows_per_gpu": rows,
                    "l2": "inputs (col = %.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
                          % (nnz_l * 4 / 1e9),
-                   "exchange": "nccl all_gather of f" if world > 1 else "none"},
+                   "exchange": {"p2p": "none: f shards peer-mapped over NVLink (CUDA IPC), neighbour "
+                                       "values read in place by the star kernel; 2 stream-ordered "
+                                       "barriers per step", "allgather": "nccl all_gather of f",
+                                "none": "none"}[args.exchange if world > 1 else "none"]},
         "roofline": {"bound": "hbm", "kernel": "star_csr_kernel", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": None, "peak_source": peak_src,

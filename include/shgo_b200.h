@@ -137,6 +137,37 @@ SHGO_B200_API int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t 
                             const uint8_t *feasible, uint64_t row0, uint64_t rows,
                             uint64_t nnz_hint, uint8_t *is_min, uint64_t *nfev, void *stream);
 
+/* ---- multi-GPU star test ------------------------------------------------------
+ * The f vector lives in `nshards` equal shards of rows_per_shard values, shard g on GPU g; each GPU
+ * classifies its own rows [row0, row0+rows), row0 = my_shard * rows_per_shard, in two phases:
+ *
+ *  1. shgo_b200_star_csr_local: the single-GPU kernel on the GPU's OWN shard of f (f_own, indexed
+ *     by row - row0).  Neighbours owned by other GPUs are skipped.  flags[r] = 0 (not a minimiser),
+ *     1 (minimiser, all neighbours local) or 2 (candidate: passed every local neighbour, has remote
+ *     ones).  Needs no communication and no barrier; also counts nfev like shgo_b200_star_csr_nfev.
+ *  2. shgo_b200_star_csr_remote: compacts the candidates (a few percent of the rows) and tests their
+ *     remote neighbours, reading f in place from the peer-mapped shards (f_shards: DEVICE array of
+ *     nshards base pointers, own shard = f_own, others mapped over NVLink with shgo_b200_ipc_*).
+ *     Only 8 bytes per remote neighbour of a candidate cross NVLink; there is no exchange of f.
+ *     Rewrites the 2s in flags to 0 / 1.  All ranks must have finished writing f before any rank
+ *     starts phase 2 (caller's barrier).  cand_cap: room for candidate indices (rows is always
+ *     enough); tmp: shgo_b200_star_remote_workspace(rows, cand_cap) bytes.
+ * row_ptr / col are this shard's slices addressed with GLOBAL row ids / offsets (virtual bases). */
+SHGO_B200_API int shgo_b200_star_csr_local(const int64_t *row_ptr, const int32_t *col, const double *f_own,
+                             const uint8_t *feasible, uint64_t row0, uint64_t rows,
+                             uint64_t nnz_hint, uint8_t *flags, uint64_t *nfev, void *stream);
+SHGO_B200_API size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap);
+SHGO_B200_API int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col,
+                              const double *const *f_shards, const double *f_own, int nshards,
+                              uint64_t rows_per_shard, int my_shard, uint64_t rows, uint8_t *flags,
+                              uint64_t cand_cap, void *tmp, size_t tmp_bytes, void *stream);
+/* cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle / cudaFree;
+ * handle64 is the 64-byte cudaIpcMemHandle_t to ship to the peer processes. */
+SHGO_B200_API int shgo_b200_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64);
+SHGO_B200_API int shgo_b200_ipc_open(const unsigned char *handle64, void **ptr);
+SHGO_B200_API int shgo_b200_ipc_close(void *ptr);
+SHGO_B200_API int shgo_b200_ipc_free(void *ptr);
+
 /* ---- a7: pool extraction ----------------------------------------------------------------------------
  * Replaces the scan over HC.V.cache in SHGO.minimizers (reference _shgo.py:1109-1157):
  * idx_out receives base + i for every i with is_min[i] != 0, ascending; *count the total.

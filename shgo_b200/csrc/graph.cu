@@ -1,5 +1,7 @@
 // graph.cu -- K3 (vertex-face mesh -> CSR), K4 (CSR star test), pool compaction, arg-min and
 // nfev bookkeeping.  Integer / byte work bound by HBM; no tensor cores involved.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace shgo_b200 {
@@ -40,16 +42,28 @@ __device__ __forceinline__ void cp_async_wait_all()
 // One round of the row walk on the staged slice: the next W neighbours (32-bit local indices; the
 // tail of a row is handled by clamping, so a short row simply re-tests its last neighbour instead
 // of paying for per-entry predicates and +inf selects).
-template <int W>
+// LOCAL (multi-GPU, phase 1): f is this GPU's shard, indexed by row - row0; neighbours owned by
+// another GPU are skipped here and remembered in `remote`.
+template <int W, bool LOCAL>
 __device__ __forceinline__ bool star_round(const int32_t *__restrict__ sc, const double *__restrict__ f,
-                                           double fv, int &k, int last)
+                                           double fv, int &k, int last, uint32_t row0, uint32_t rows,
+                                           bool &remote)
 {
     int32_t nb[W];
     double fn[W];
 #pragma unroll
     for (int u = 0; u < W; ++u) nb[u] = sc[min(k + u, last)];
 #pragma unroll
-    for (int u = 0; u < W; ++u) fn[u] = ld_nc_f64(f + nb[u]);
+    for (int u = 0; u < W; ++u) {
+        if (LOCAL) {
+            const uint32_t l = (uint32_t)nb[u] - row0;
+            const bool mine = l < rows;
+            remote = remote || !mine;
+            fn[u] = mine ? ld_nc_f64(f + l) : pos_inf();
+        } else {
+            fn[u] = ld_nc_f64(f + nb[u]);
+        }
+    }
     bool ok = true;
 #pragma unroll
     for (int u = 0; u < W; ++u) ok = ok && (fv < fn[u]);
@@ -62,8 +76,9 @@ struct StarMeta {  // what a lane knows about its row of a tile before the slice
     double fv;
     bool valid;
 };
+// f_rows: f addressed by GLOBAL row id (the caller passes the virtual base of a shard)
 __device__ __forceinline__ StarMeta star_meta(const int64_t *__restrict__ row_ptr,
-                                              const double *__restrict__ f, uint64_t row0,
+                                              const double *__restrict__ f_rows, uint64_t row0,
                                               uint64_t rows, uint64_t tile, uint64_t ntiles, int lane)
 {
     StarMeta m;
@@ -72,10 +87,15 @@ __device__ __forceinline__ StarMeta star_meta(const int64_t *__restrict__ row_pt
     const uint64_t r = row0 + (m.valid ? lr : rows);  // invalid lanes: empty row at the end
     m.b = row_ptr[r];
     m.e = m.valid ? row_ptr[r + 1] : m.b;
-    m.fv = m.valid ? ld_nc_f64(f + r) : 0.0;
+    m.fv = m.valid ? ld_nc_f64(f_rows + r) : 0.0;
     return m;
 }
 
+// LOCAL = false: `f` is the whole vector, flags are 0 / 1.
+// LOCAL = true : `f` is this GPU's shard (rows row0 .. row0+rows); a row that passed every LOCAL
+//                neighbour but also has neighbours on other GPUs gets flag 2 ("candidate") and is
+//                finished by star_remote_kernel.
+template <bool LOCAL>
 __global__ void __launch_bounds__(kStarThreads, 5)
 star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                 const double *__restrict__ f, const uint8_t *__restrict__ feasible, uint64_t row0,
@@ -88,16 +108,18 @@ star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__
     const uint64_t ntiles = (rows + 31) >> 5;
     const uint64_t gw = ((uint64_t)blockIdx.x * kStarThreads + threadIdx.x) >> 5;
     const uint64_t nw = ((uint64_t)gridDim.x * kStarThreads) >> 5;
+    const double *f_rows = LOCAL ? f - row0 : f;
     unsigned present_feasible = 0;
     // row_ptr / f of the NEXT tile are fetched while the current one is walked
-    StarMeta cur = star_meta(row_ptr, f, row0, rows, gw, ntiles, lane);
+    StarMeta cur = star_meta(row_ptr, f_rows, row0, rows, gw, ntiles, lane);
     for (uint64_t tile = gw; tile < ntiles; tile += nw) {
         const uint64_t lr = (tile << 5) + lane;
         const int64_t b = cur.b, e = cur.e;
         const double fv = cur.fv;
         const bool valid = cur.valid;
         const int64_t s0 = __shfl_sync(0xffffffffu, b, 0), s1 = __shfl_sync(0xffffffffu, e, 31);
-        const int64_t s0a = s0 & ~(int64_t)3;
+        // align the slice start down to a 16-byte ADDRESS (col may be a shard's virtual base)
+        const int64_t s0a = s0 - (int64_t)((reinterpret_cast<uintptr_t>(col + s0) >> 2) & 3);
         const bool staged = s1 - s0a <= cap_w;
         if (staged) {
             const int len = (int)(s1 - s0a);
@@ -106,28 +128,86 @@ star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__
             for (int v = lane; v < nvec; v += 32) cp_async16(sc + (v << 2), src + (v << 2));
             for (int k = (nvec << 2) + lane; k < len; k += 32) sc[k] = __ldg(src + k);
         }
-        cur = star_meta(row_ptr, f, row0, rows, tile + nw, ntiles, lane);
+        cur = star_meta(row_ptr, f_rows, row0, rows, tile + nw, ntiles, lane);
         bool ok = valid && e > b;
+        bool remote = false;
         if (nfev != nullptr && ok && (feasible == nullptr || feasible[lr])) ++present_feasible;
         if (staged) {
             cp_async_wait_all();
             __syncwarp();
-            const int lb = (int)(b - s0a), le = (int)(e - s0a);
-            int k = lb;
-            const int last = le - 1;
-            if (ok) ok = star_round<4>(sc, f, fv, k, last);
-            if (ok && k < le) ok = star_round<8>(sc, f, fv, k, last);
-            while (ok && k < le) ok = star_round<16>(sc, f, fv, k, last);
+            int k = (int)(b - s0a);
+            const int le = (int)(e - s0a), last = le - 1;
+            const uint32_t r0 = (uint32_t)row0, nr = (uint32_t)rows;
+            if (ok) ok = star_round<4, LOCAL>(sc, f, fv, k, last, r0, nr, remote);
+            if (ok && k < le) ok = star_round<8, LOCAL>(sc, f, fv, k, last, r0, nr, remote);
+            while (ok && k < le) ok = star_round<16, LOCAL>(sc, f, fv, k, last, r0, nr, remote);
         } else {
-            for (int64_t k = b; k < e && ok; ++k) ok = fv < ld_nc_f64(f + __ldg(col + k));
+            for (int64_t k = b; k < e && ok; ++k) {
+                const int32_t w = __ldg(col + k);
+                if (LOCAL) {
+                    const uint32_t l = (uint32_t)w - (uint32_t)row0;
+                    if (l < (uint32_t)rows) ok = fv < ld_nc_f64(f + l); else remote = true;
+                } else {
+                    ok = fv < ld_nc_f64(f + w);
+                }
+            }
         }
-        if (valid) is_min[lr] = ok ? 1 : 0;
+        if (valid) is_min[lr] = ok ? (LOCAL && remote ? 2 : 1) : 0;
         __syncwarp();  // the slice is rewritten by the next tile
     }
     if (nfev != nullptr) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) present_feasible += __shfl_down_sync(0xffffffffu, present_feasible, o);
         if (lane == 0 && present_feasible) atomicAdd(nfev, (unsigned long long)present_feasible);
+    }
+}
+
+// ---- multi-GPU, phase 2 ---------------------------------------------------------------------------
+// f lives in N equal shards, one per GPU, all mapped into this process over NVLink (CUDA IPC).
+// One thread per CANDIDATE row (compacted list: a few percent of the rows) re-reads its neighbour
+// list and tests only the neighbours owned by other GPUs, reading their f in place through the
+// peer pointers -- plain ld.global over NVLink, all candidates in flight at once, so the link
+// latency is hidden by parallelism and only 8 bytes per remote neighbour of a candidate cross it.
+struct ShardedF {
+    const double *const *shards;  // device array of nshards base pointers (own shard = local HBM)
+    uint32_t rows_per_shard;
+    __device__ __forceinline__ double operator()(int32_t w) const
+    {
+        const uint32_t q = (uint32_t)w / rows_per_shard;
+        const double *p = shards[q] + ((uint32_t)w - q * rows_per_shard);
+        double v;
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+        return v;
+    }
+};
+
+__global__ void __launch_bounds__(256)
+star_remote_kernel(const int64_t *__restrict__ cand, const uint64_t *__restrict__ ncand, uint64_t cap,
+                   const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col, ShardedF facc,
+                   const double *__restrict__ f_own, uint64_t row0, uint64_t rows,
+                   uint8_t *__restrict__ is_min)
+{
+    uint64_t n = *ncand;
+    if (n > cap) n = cap;
+    for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n;
+         c += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t lr = (uint64_t)cand[c];
+        const uint64_t r = row0 + lr;
+        const double fv = ld_nc_f64(f_own + lr);
+        bool ok = true;
+        const int64_t e = row_ptr[r + 1];
+        for (int64_t k = row_ptr[r]; k < e && ok; k += 4) {
+            int32_t w[4];
+            double fn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) w[u] = __ldg(col + (k + u < e ? k + u : e - 1));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                fn[u] = ((uint32_t)w[u] - (uint32_t)row0 < (uint32_t)rows) ? pos_inf() : facc(w[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ok = ok && (fv < fn[u]);
+        }
+        is_min[lr] = ok ? 1 : 0;
     }
 }
 
@@ -140,16 +220,19 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 16;
 constexpr int kScanBlock = kScanThreads * kScanItems;  // 4096
 
+// uint8 flags count 1 when they equal `match` (match == 0: when non-zero); uint32 items count as is
 template <class T>
 __device__ __forceinline__ uint32_t load_items(const T *in, uint64_t base, uint64_t n,
-                                               uint32_t (&v)[kScanItems])
+                                               uint32_t (&v)[kScanItems], int match = 0)
 {
     uint32_t s = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) {
         uint64_t k = base + i;
-        v[i] = k < n ? (uint32_t)(in[k] != 0 ? (sizeof(T) == 1 ? 1u : (uint32_t)in[k]) : 0u) : 0u;
-        s += v[i];
+        uint32_t x = k < n ? (uint32_t)in[k] : 0u;
+        if (sizeof(T) == 1) x = match ? (x == (uint32_t)match) : (x != 0);
+        v[i] = x;
+        s += x;
     }
     return s;
 }
@@ -189,11 +272,11 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t *t
 
 template <class T>
 __global__ void __launch_bounds__(kScanThreads)
-block_sum_kernel(const T *__restrict__ in, uint64_t n, uint64_t *__restrict__ sums)
+block_sum_kernel(const T *__restrict__ in, uint64_t n, uint64_t *__restrict__ sums, int match)
 {
     uint32_t v[kScanItems];
     uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
-    uint32_t s = load_items(in, base, n, v);
+    uint32_t s = load_items(in, base, n, v, match);
     uint32_t total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) sums[blockIdx.x] = total;
@@ -242,11 +325,11 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(uint64_t *sums, uint64_
 // pool compaction, pass 3: ascending indices of the non-zero flags
 __global__ void __launch_bounds__(kScanThreads)
 compact_scatter_kernel(const uint8_t *__restrict__ flags, uint64_t n, const uint64_t *__restrict__ offs,
-                       int64_t base_index, int64_t *__restrict__ idx_out, uint64_t cap)
+                       int64_t base_index, int64_t *__restrict__ idx_out, uint64_t cap, int match)
 {
     uint32_t v[kScanItems];
     const uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems;
-    uint32_t s = load_items(flags, base, n, v);
+    uint32_t s = load_items(flags, base, n, v, match);
     uint32_t total;
     uint32_t ex = block_exclusive_scan(s, &total);
     if (s == 0) return;
@@ -481,8 +564,19 @@ static inline unsigned grid_for(uint64_t items, int threads, int per_sm)
 
 using namespace shgo_b200;
 
-extern "C" {
+static size_t star_smem_bytes(uint64_t rows, uint64_t nnz_hint, long *cap_out)
+{
+    // staging slice per warp: 32 rows * ~1.125 * mean degree (+ alignment slack), 16-byte multiple
+    double mean_deg = nnz_hint ? (double)nnz_hint / (double)rows : 32.0;
+    long cap = (long)(mean_deg * 32.0 * 1.125) + 16;
+    if (cap < 256) cap = 256;
+    if (cap > 6144) cap = 6144;  // 24 KB per warp at most (1 CTA of 8 warps per SM)
+    cap = (cap + 63) & ~63L;
+    *cap_out = cap;
+    return (size_t)cap * kStarWarps * sizeof(int32_t);
+}
 
+template <bool LOCAL>
 static int launch_star(const int64_t *row_ptr, const int32_t *col, const double *f,
                        const uint8_t *feasible, uint64_t row0, uint64_t rows, uint64_t nnz_hint,
                        uint8_t *is_min, uint64_t *nfev, cudaStream_t st)
@@ -490,15 +584,10 @@ static int launch_star(const int64_t *row_ptr, const int32_t *col, const double 
     if (nfev) SHGO_CUDA_TRY(cudaMemsetAsync(nfev, 0, sizeof(uint64_t), st));
     if (rows == 0) return SHGO_B200_OK;
     SHGO_REQUIRE(row_ptr && f && is_min, "null pointer");
-    SHGO_REQUIRE((reinterpret_cast<uintptr_t>(col) & 15) == 0, "col must be 16-byte aligned");
-    // staging slice per warp: 32 rows * ~1.25 * mean degree (+ alignment slack), 16-byte multiple
-    double mean_deg = nnz_hint ? (double)nnz_hint / (double)rows : 32.0;
-    long cap = (long)(mean_deg * 32.0 * 1.125) + 16;
-    if (cap < 256) cap = 256;
-    if (cap > 6144) cap = 6144;  // 24 KB per warp at most (1 CTA of 8 warps per SM)
-    cap = (cap + 63) & ~63L;
-    const size_t smem = (size_t)cap * kStarWarps * sizeof(int32_t);
-    auto kern = star_csr_kernel;
+    SHGO_REQUIRE((reinterpret_cast<uintptr_t>(col) & 3) == 0, "col must be 4-byte aligned");
+    long cap = 0;
+    const size_t smem = star_smem_bytes(rows, nnz_hint, &cap);
+    auto kern = star_csr_kernel<LOCAL>;
     if (smem > 48 * 1024)
         SHGO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int occ = 0;
@@ -507,16 +596,35 @@ static int launch_star(const int64_t *row_ptr, const int32_t *col, const double 
     uint64_t tiles = (rows + kStarThreads - 1) / kStarThreads;
     uint64_t grid = (uint64_t)sm_count() * occ;
     if (grid > tiles) grid = tiles;
-    kern<<<(unsigned)grid, kStarThreads, smem, st>>>(
-        row_ptr, col, f, feasible, row0, rows, (int)cap, is_min, reinterpret_cast<unsigned long long *>(nfev));
+    kern<<<(unsigned)grid, kStarThreads, smem, st>>>(row_ptr, col, f, feasible, row0, rows, (int)cap, is_min,
+                                                    reinterpret_cast<unsigned long long *>(nfev));
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;
 }
 
+static int compact_impl(const uint8_t *flags, uint64_t n, int match, int64_t base, int64_t *idx_out,
+                        uint64_t cap, uint64_t *count, void *tmp, cudaStream_t st)
+{
+    if (n == 0) {
+        SHGO_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint64_t), st));
+        return SHGO_B200_OK;
+    }
+    uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
+    uint64_t *sums = static_cast<uint64_t *>(tmp);
+    block_sum_kernel<uint8_t><<<(unsigned)nb, kScanThreads, 0, st>>>(flags, n, sums, match);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, count);
+    compact_scatter_kernel<<<(unsigned)nb, kScanThreads, 0, st>>>(flags, n, sums, base, idx_out, cap, match);
+    SHGO_CUDA_TRY(cudaGetLastError());
+    return SHGO_B200_OK;
+}
+
+extern "C" {
+
 int shgo_b200_star_csr(const int64_t *row_ptr, const int32_t *col, const double *f, uint64_t row0,
                        uint64_t rows, uint64_t nnz_hint, uint8_t *is_min, void *stream)
 {
-    return launch_star(row_ptr, col, f, nullptr, row0, rows, nnz_hint, is_min, nullptr, as_stream(stream));
+    return launch_star<false>(row_ptr, col, f, nullptr, row0, rows, nnz_hint, is_min, nullptr,
+                              as_stream(stream));
 }
 
 int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t *col, const double *f,
@@ -524,7 +632,89 @@ int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t *col, const do
                             uint8_t *is_min, uint64_t *nfev, void *stream)
 {
     SHGO_REQUIRE(nfev, "null nfev");
-    return launch_star(row_ptr, col, f, feasible, row0, rows, nnz_hint, is_min, nfev, as_stream(stream));
+    return launch_star<false>(row_ptr, col, f, feasible, row0, rows, nnz_hint, is_min, nfev, as_stream(stream));
+}
+
+int shgo_b200_star_csr_local(const int64_t *row_ptr, const int32_t *col, const double *f_own,
+                             const uint8_t *feasible, uint64_t row0, uint64_t rows, uint64_t nnz_hint,
+                             uint8_t *flags, uint64_t *nfev, void *stream)
+{
+    SHGO_REQUIRE(row0 + rows <= 0x7fffffffull, "row range out of int32");
+    return launch_star<true>(row_ptr, col, f_own, feasible, row0, rows, nnz_hint, flags, nfev,
+                             as_stream(stream));
+}
+
+size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap)
+{
+    return align256(cand_cap * sizeof(int64_t)) + shgo_b200_compact_workspace(rows) + align256(16);
+}
+
+int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const double *const *f_shards,
+                              const double *f_own, int nshards, uint64_t rows_per_shard, int my_shard,
+                              uint64_t rows, uint8_t *flags, uint64_t cand_cap, void *tmp, size_t tmp_bytes,
+                              void *stream)
+{
+    cudaStream_t st = as_stream(stream);
+    if (rows == 0) return SHGO_B200_OK;
+    SHGO_REQUIRE(row_ptr && f_shards && f_own && flags && tmp, "null pointer");
+    SHGO_REQUIRE(nshards >= 1 && my_shard >= 0 && my_shard < nshards, "bad shard index");
+    SHGO_REQUIRE(rows_per_shard >= 1 && rows_per_shard <= 0x7fffffffull && rows <= rows_per_shard,
+                 "bad shard size");
+    if (tmp_bytes < shgo_b200_star_remote_workspace(rows, cand_cap))
+        return fail(SHGO_B200_ERR_WORKSPACE, "remote-phase workspace: need %zu bytes, got %zu",
+                    shgo_b200_star_remote_workspace(rows, cand_cap), tmp_bytes);
+    unsigned char *p = static_cast<unsigned char *>(tmp);
+    int64_t *cand = reinterpret_cast<int64_t *>(p);
+    p += align256(cand_cap * sizeof(int64_t));
+    void *ctmp = p;
+    p += shgo_b200_compact_workspace(rows);
+    uint64_t *ncand = reinterpret_cast<uint64_t *>(p);
+    if (int rc = compact_impl(flags, rows, /*match=*/2, 0, cand, cand_cap, ncand, ctmp, st)) return rc;
+    ShardedF facc{f_shards, (uint32_t)rows_per_shard};
+    const uint64_t row0 = (uint64_t)my_shard * rows_per_shard;
+    // candidates beyond cand_cap would be left with flag 2; callers size cand_cap = rows to be safe
+    star_remote_kernel<<<sm_count() * 8, 256, 0, st>>>(cand, ncand, cand_cap, row_ptr, col, facc, f_own, row0,
+                                                     rows, flags);
+    SHGO_CUDA_TRY(cudaGetLastError());
+    return SHGO_B200_OK;
+}
+
+// ---- CUDA IPC plumbing for the peer-mapped f shards ---------------------------------------------
+int shgo_b200_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64)
+{
+    SHGO_REQUIRE(ptr && handle64 && bytes > 0, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    SHGO_CUDA_TRY(cudaMalloc(ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        return fail(SHGO_B200_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    return SHGO_B200_OK;
+}
+
+int shgo_b200_ipc_open(const unsigned char *handle64, void **ptr)
+{
+    SHGO_REQUIRE(ptr && handle64, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SHGO_CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SHGO_B200_OK;
+}
+
+int shgo_b200_ipc_close(void *ptr)
+{
+    if (ptr) SHGO_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+    return SHGO_B200_OK;
+}
+
+int shgo_b200_ipc_free(void *ptr)
+{
+    if (ptr) SHGO_CUDA_TRY(cudaFree(ptr));
+    return SHGO_B200_OK;
 }
 
 size_t shgo_b200_compact_workspace(uint64_t n)
@@ -542,18 +732,7 @@ int shgo_b200_compact_pool(const uint8_t *is_min, uint64_t n, int64_t base, int6
     if (tmp_bytes < shgo_b200_compact_workspace(n))
         return fail(SHGO_B200_ERR_WORKSPACE, "compact workspace: need %zu bytes, got %zu",
                     shgo_b200_compact_workspace(n), tmp_bytes);
-    cudaStream_t st = as_stream(stream);
-    if (n == 0) {
-        SHGO_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint64_t), st));
-        return SHGO_B200_OK;
-    }
-    uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
-    uint64_t *sums = static_cast<uint64_t *>(tmp);
-    block_sum_kernel<uint8_t><<<(unsigned)nb, kScanThreads, 0, st>>>(is_min, n, sums);
-    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, count);
-    compact_scatter_kernel<<<(unsigned)nb, kScanThreads, 0, st>>>(is_min, n, sums, base, idx_out, cap);
-    SHGO_CUDA_TRY(cudaGetLastError());
-    return SHGO_B200_OK;
+    return compact_impl(is_min, n, /*match=*/1, base, idx_out, cap, count, tmp, as_stream(stream));
 }
 
 size_t shgo_b200_csr_workspace(uint64_t S, int dp1, uint64_t n)
@@ -602,7 +781,7 @@ int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, 
     if (S > 0)
         edge_insert_kernel<<<grid_for(S, 256, 8), 256, 0, st>>>(simplices, S, dp1, n, table, slots - 1,
                                                                 deg, bad);
-    block_sum_kernel<uint32_t><<<(unsigned)nb, kScanThreads, 0, st>>>(deg, n, sums);
+    block_sum_kernel<uint32_t><<<(unsigned)nb, kScanThreads, 0, st>>>(deg, n, sums, 0);
     scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, nnz);
     // n+1 outputs: one more block when n is a multiple of the block size
     rowptr_kernel<<<(unsigned)(n / kScanBlock + 1), kScanThreads, 0, st>>>(deg, n, sums, row_ptr);

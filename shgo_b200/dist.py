@@ -1,0 +1,180 @@
+"""Multi-GPU Sobol path: one process per GPU (torch.distributed), points sharded by index range.
+
+SURVEY.md section 8(e): rank r of G owns Sobol indices / graph rows [r n/G, (r+1) n/G).  Point generation
+has a closed-form skip-ahead, so every shard generates and evaluates locally with no communication.
+The star test needs neighbours' f across shards.  Two exchanges are implemented:
+
+  'p2p'        (default on GPUs) the f shards are allocated with cudaMalloc, exported with CUDA IPC and
+               peer-mapped into every rank over NVLink.  Phase 1 classifies every row against its
+               LOCAL neighbours (no communication); phase 2 finishes the few rows that survived --
+               their remote neighbours' f values are read in place over NVLink by the kernel itself,
+               8 bytes per remote neighbour of a candidate.  Collectives are used for plumbing only
+               (two stream-ordered barriers per iteration, pool gather).
+  'allgather'  one all_gather of the f vector (NCCL on GPUs; gloo in the CPU tests), then the
+               single-GPU star kernel on the rank's rows.  8 n (G-1)/G bytes received per GPU.
+
+torch.distributed is plumbing here; the kernels are the ones of libshgo_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import hotpath as hp
+
+
+class _RawCudaBuffer:
+    """cudaMalloc'ed memory exposed to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, nelem, typestr):
+        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+class PeerMappedVector:
+    """A float64 vector of `rows` elements per rank, readable by every rank's kernels."""
+
+    def __init__(self, rows, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows = rows
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.call("shgo_b200_ipc_alloc", rows * 8, ctypes.byref(ptr), handle)
+        self.own_ptr = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.peer_ptrs = []
+        self._opened = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.peer_ptrs.append(self.own_ptr)
+            else:
+                p = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                _lib.call("shgo_b200_ipc_open", buf, ctypes.byref(p))
+                self.peer_ptrs.append(p.value)
+                self._opened.append(p.value)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.table = torch.tensor(self.peer_ptrs, dtype=torch.int64, device=dev)
+        self.local = torch.as_tensor(_RawCudaBuffer(self.own_ptr, rows, "<f8"), device=dev)
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for p in self._opened:
+            _lib.call("shgo_b200_ipc_close", p)
+        self._opened = []
+        dist.barrier(group=self.group)
+        if self.own_ptr:
+            _lib.call("shgo_b200_ipc_free", self.own_ptr)
+            self.own_ptr = None
+
+
+def _all_gather(out, mine, group):
+    try:
+        dist.all_gather_into_tensor(out, mine, group=group)
+    except (RuntimeError, NotImplementedError):      # backends without the flat variant
+        parts = list(out.chunk(dist.get_world_size(group)))
+        dist.all_gather(parts, mine.contiguous(), group=group)
+
+
+def shard_range(n, world, rank):
+    """rows [row0, row0 + rows) of `rank`; n must divide evenly (power-of-two problem sizes)."""
+    if n % world:
+        raise ValueError("n = %d is not divisible by the number of ranks %d" % (n, world))
+    rows = n // world
+    return rank * rows, rows
+
+
+class ShardedSobolIteration:
+    """One shgo iteration of the Sobol hot path over all ranks of `group`.
+
+    row_ptr_local / col_local: this rank's CSR rows; row_ptr_local holds GLOBAL offsets starting at
+    row_ptr[row0] (i.e. a slice of the global row_ptr), col_local the matching slice of col with
+    GLOBAL vertex ids."""
+
+    def __init__(self, functor, gset, tab, n, row_ptr_local, col_local, group=None, exchange="p2p",
+                 pool_cap=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.functor, self.gset, self.tab, self.n = functor, gset, tab, n
+        self.row0, self.rows = shard_range(n, self.world, self.rank)
+        self.exchange = exchange if self.world > 1 else "none"
+        self.row_ptr, self.col = row_ptr_local, col_local
+        dev = row_ptr_local.device
+        self.dev = dev
+        self.nnz_local = col_local.numel()
+        self.feas = torch.empty(self.rows, dtype=torch.uint8, device=dev)
+        self.is_min = torch.empty(self.rows, dtype=torch.uint8, device=dev)
+        self.nfev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.work = hp.PoolWorkspace(self.rows, self.rows if pool_cap is None else pool_cap, dev)
+        self._token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.peer = None
+        if self.exchange == "p2p":
+            self.peer = PeerMappedVector(self.rows, group)
+            self.f_my = self.peer.local
+            self.f_all = None
+            ws = _lib.lib().shgo_b200_star_remote_workspace(self.rows, self.rows)
+            self._remote_tmp = torch.empty(ws, dtype=torch.uint8, device=dev)
+        else:
+            self.f_all = torch.empty(n if self.world > 1 else self.rows, dtype=torch.float64, device=dev)
+            self.f_my = self.f_all[self.row0:self.row0 + self.rows] if self.world > 1 else self.f_all
+
+    def _barrier(self):
+        # stream-ordered (NCCL all-reduce of one int): no host synchronisation
+        dist.all_reduce(self._token, group=self.group)
+
+    def step(self, events=None):
+        hp.eval_sobol(self.functor, self.gset, self.tab, self.row0, self.rows, f=self.f_my, feasible=self.feas)
+        if events:
+            events[0].record()
+        if self.exchange == "p2p":
+            # phase 1 needs nobody else; the barrier (every shard of f complete before anyone reads
+            # it remotely) is only waited for after it
+            hp.star_csr_local(self.row_ptr, self.col, self.row0, self.f_my, self.feas, self.is_min, self.nfev)
+            self._barrier()
+            hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table, self.peer.own_ptr,
+                               self.world, self.rows, self.rank, self.is_min, self._remote_tmp, self.rows)
+        else:
+            if self.exchange == "allgather":
+                _all_gather(self.f_all, self.f_my, self.group)
+            f_all = self.f_all
+            if self.world == 1:        # single rank: f is the shard itself, addressed globally
+                hp.star_csr(self.row_ptr, self.col, f_all, is_min=self.is_min, feasible=self.feas,
+                            nfev=self.nfev)
+            else:
+                hp.star_csr_shard(self.row_ptr, self.col, self.row0, f_all, self.feas, self.is_min, self.nfev)
+        if events:
+            events[1].record()
+        hp.compact_pool(self.is_min, base=self.row0, work=self.work)
+        if self.exchange == "p2p":
+            self._barrier()            # nobody overwrites f while a peer may still be reading it
+
+    def local_pool(self):
+        c = int(self.work.count[0].item())
+        return self.work.idx[:min(c, self.work.cap)]
+
+    def global_pool(self):
+        """ascending pool indices of the whole problem, on every rank (pools are small in real use)"""
+        mine = self.local_pool().cpu().numpy()
+        if self.world == 1:
+            return mine
+        parts = [None] * self.world
+        dist.all_gather_object(parts, mine, group=self.group)
+        return np.concatenate(parts)
+
+    def global_nfev(self):
+        t = self.nfev.clone()
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None

@@ -31,7 +31,14 @@ def sobol_points(tab, k0, n, layout="soa", out=None):
 
 def eval_sobol(functor, gset, tab, k0, n, f=None, feasible=None, want_feasible=True):
     fo, fe = orc.sobol_eval(tab.sv_host, _FN[functor], _GN[gset], k0, n, tab.lb_host, tab.ub_host)
-    return torch.from_numpy(fo), torch.from_numpy(fe)
+    fo, fe = torch.from_numpy(fo), torch.from_numpy(fe)
+    if f is not None:
+        f.copy_(fo)
+        fo = f
+    if feasible is not None:
+        feasible.copy_(fe)
+        fe = feasible
+    return fo, fe
 
 
 def eval_points(functor, gset, x_soa, f=None, feasible=None):
@@ -72,7 +79,38 @@ def star_csr(row_ptr, col, f, row0=0, rows=None, is_min=None, feasible=None, nfe
     return torch.from_numpy(out)
 
 
+def star_csr_shard(row_ptr_local, col_local, row0, f_all, feasible, is_min, nfev):
+    rp = row_ptr_local.numpy()
+    rows = len(rp) - 1
+    rp0 = rp - rp[0]
+    out = np.empty(rows, np.uint8)
+    fh, c = f_all.numpy(), col_local.numpy()
+    for r in range(rows):
+        nb = c[rp0[r]:rp0[r + 1]]
+        out[r] = 1 if len(nb) and np.all(fh[row0 + r] < fh[nb]) else 0
+    is_min.copy_(torch.from_numpy(out))
+    nfev[0] = int(np.sum((np.diff(rp) > 0) & (feasible.numpy() != 0)))
+    return is_min
+
+
+class PoolWorkspace:
+    def __init__(self, n, cap, device):
+        self.cap = cap
+        self.idx = torch.empty(max(cap, 1), dtype=torch.int64)
+        self.count = torch.zeros(2, dtype=torch.int64)
+
+
 def compact_pool(is_min, base=0, cap=None, work=None):
+    if work is not None:
+        idx = orc.compact_pool(np.ascontiguousarray(is_min.numpy())) + base
+        work.count[0] = len(idx)
+        m = min(len(idx), work.cap)
+        work.idx[:m] = torch.from_numpy(idx[:m])
+        return work.idx, work.count[0]
+    return _compact_pool(is_min, base)
+
+
+def _compact_pool(is_min, base=0):
     idx = orc.compact_pool(np.ascontiguousarray(is_min.numpy())) + base
     return torch.from_numpy(idx), torch.tensor(len(idx))
 
@@ -109,7 +147,7 @@ def install(monkeypatch):
     """Patch shgo_b200.hotpath in place (functions are looked up as attributes at call time)."""
     from shgo_b200 import hotpath as hp
     for name in ("SobolTables", "sobol_points", "eval_sobol", "eval_points", "mask_infeasible",
-                 "csr_from_simplices", "first_seen", "star_csr", "compact_pool", "argmin", "lattice_eval",
+                 "csr_from_simplices", "first_seen", "star_csr", "star_csr_shard", "PoolWorkspace", "compact_pool", "argmin", "lattice_eval",
                  "lattice_coords", "lattice_star"):
         monkeypatch.setattr(hp, name, globals()[name])
     monkeypatch.setattr(hp, "_require_cuda", lambda: None)
