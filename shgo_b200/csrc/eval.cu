@@ -48,16 +48,30 @@ eval_kernel(typename SrcT<F::P>::Params sp, int d, double *__restrict__ f,
         double fv[P];
         uint32_t ok;
         F::run(src, d, fv, ok);
+        uint64_t first;
+        if (src.full_tile(first)) {  // interior tile: no per-point range checks
+            double *fp = f + first + threadIdx.x;
+            uint8_t *gp = feasible ? feasible + first + threadIdx.x : nullptr;
 #pragma unroll
-        for (int i = 0; i < P; ++i) {
-            uint64_t idx;
-            if (src.valid(i, idx)) {
-                bool feas = (ok >> i) & 1u;
+            for (int i = 0; i < P; ++i) {
+                const bool feas = (ok >> i) & 1u;
                 double v = fv[i];
                 // infeasible -> inf (_vertex.py:334); NaN objective -> inf (_vertex.py:351-352)
                 if (!feas || v != v) v = pos_inf();
-                f[idx] = v;
-                if (feasible) feasible[idx] = feas ? 1 : 0;
+                fp[i * kEvalThreads] = v;
+                if (gp) gp[i * kEvalThreads] = feas ? 1 : 0;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                uint64_t idx;
+                if (src.valid(i, idx)) {
+                    const bool feas = (ok >> i) & 1u;
+                    double v = fv[i];
+                    if (!feas || v != v) v = pos_inf();
+                    f[idx] = v;
+                    if (feasible) feasible[idx] = feas ? 1 : 0;
+                }
             }
         }
     }

@@ -134,6 +134,12 @@ struct SobolSrc {
         out = k - k0;
         return k >= k0 && k < k0 + n;
     }
+    // whole tile inside the requested range?  out = output index of the tile's first point
+    __device__ __forceinline__ bool full_tile(uint64_t &out) const
+    {
+        out = tile_first - k0;
+        return tile_first >= k0 && tile_first + kTile <= k0 + n;
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -167,6 +173,11 @@ struct SoaSrc {
     {
         out = tile_first + (uint64_t)i * kEvalThreads + threadIdx.x;
         return out < n;
+    }
+    __device__ __forceinline__ bool full_tile(uint64_t &out) const
+    {
+        out = tile_first;
+        return tile_first + kTile <= n;
     }
 };
 
@@ -244,6 +255,11 @@ struct LatticeSrc {
     {
         out = tile_first + (uint64_t)i * kEvalThreads + threadIdx.x;
         return out < nv;
+    }
+    __device__ __forceinline__ bool full_tile(uint64_t &out) const
+    {
+        out = tile_first;
+        return tile_first + kTile <= nv;
     }
 };
 
