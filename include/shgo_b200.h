@@ -201,9 +201,12 @@ SHGO_B200_API int shgo_b200_lattice_eval(int functor, int gset, int d, int gen, 
 /* coordinates of vertices v0 .. v0+nv-1, SoA [d][ld] */
 SHGO_B200_API int shgo_b200_lattice_coords(int d, int gen, const double *tab, uint64_t v0, uint64_t nv,
                              double *x_soa, uint64_t ld, void *stream);
-/* implicit-adjacency star test over vertices v0 .. v0+nv-1; f is the whole vector */
+/* implicit-adjacency star test over vertices v0 .. v0+nv-1; f is the whole vector.
+ * tmp: shgo_b200_lattice_star_workspace(nv) bytes (list of the few vertices whose star has to be
+ * enumerated in full by a whole thread block). */
+SHGO_B200_API size_t shgo_b200_lattice_star_workspace(uint64_t nv);
 SHGO_B200_API int shgo_b200_lattice_star(int d, int gen, const double *f, uint64_t v0, uint64_t nv,
-                           uint8_t *is_min, void *stream);
+                           uint8_t *is_min, void *tmp, size_t tmp_bytes, void *stream);
 
 /* ---- host-buffer convenience path (what bench.py's `e2e` times) ---------------------------------
  * One shgo iteration of the Sobol path with HOST inputs and outputs: uploads the CSR (pinned or

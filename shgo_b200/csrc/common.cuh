@@ -33,6 +33,10 @@ int fail(int code, const char *fmt, ...);
 // sm count of the current device (cached per device); persistent grids are sized from it
 int sm_count();
 
+// ordered compaction of the flags equal to `match` (graph.cu); tmp: shgo_b200_compact_workspace(n)
+int compact_flags(const uint8_t *flags, uint64_t n, int match, int64_t base, int64_t *idx_out,
+                  uint64_t cap, uint64_t *count, void *tmp, cudaStream_t st);
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __device__ __forceinline__ double ld_nc_f64(const double *p)

@@ -602,8 +602,8 @@ static int launch_star(const int64_t *row_ptr, const int32_t *col, const double 
     return SHGO_B200_OK;
 }
 
-static int compact_impl(const uint8_t *flags, uint64_t n, int match, int64_t base, int64_t *idx_out,
-                        uint64_t cap, uint64_t *count, void *tmp, cudaStream_t st)
+int shgo_b200::compact_flags(const uint8_t *flags, uint64_t n, int match, int64_t base, int64_t *idx_out,
+                             uint64_t cap, uint64_t *count, void *tmp, cudaStream_t st)
 {
     if (n == 0) {
         SHGO_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint64_t), st));
@@ -669,7 +669,7 @@ int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const 
     void *ctmp = p;
     p += shgo_b200_compact_workspace(rows);
     uint64_t *ncand = reinterpret_cast<uint64_t *>(p);
-    if (int rc = compact_impl(flags, rows, /*match=*/2, 0, cand, cand_cap, ncand, ctmp, st)) return rc;
+    if (int rc = compact_flags(flags, rows, /*match=*/2, 0, cand, cand_cap, ncand, ctmp, st)) return rc;
     ShardedF facc{f_shards, (uint32_t)rows_per_shard};
     const uint64_t row0 = (uint64_t)my_shard * rows_per_shard;
     // candidates beyond cand_cap would be left with flag 2; callers size cand_cap = rows to be safe
@@ -732,7 +732,7 @@ int shgo_b200_compact_pool(const uint8_t *is_min, uint64_t n, int64_t base, int6
     if (tmp_bytes < shgo_b200_compact_workspace(n))
         return fail(SHGO_B200_ERR_WORKSPACE, "compact workspace: need %zu bytes, got %zu",
                     shgo_b200_compact_workspace(n), tmp_bytes);
-    return compact_impl(is_min, n, /*match=*/1, base, idx_out, cap, count, tmp, as_stream(stream));
+    return compact_flags(is_min, n, /*match=*/1, base, idx_out, cap, count, tmp, as_stream(stream));
 }
 
 size_t shgo_b200_csr_workspace(uint64_t S, int dp1, uint64_t n)

@@ -258,11 +258,15 @@ def lattice_coords(d, gen, tab, v0, nv):
     return x
 
 
-def lattice_star(d, gen, f, v0=0, nv=None, is_min=None):
+def lattice_star(d, gen, f, v0=0, nv=None, is_min=None, tmp=None):
     nv = f.numel() - v0 if nv is None else nv
     if is_min is None:
         is_min = torch.empty(nv, dtype=torch.uint8, device=f.device)
-    _lib.call("shgo_b200_lattice_star", d, gen, _ptr(f), v0, nv, _ptr(is_min), _stream())
+    ws = _lib.lib().shgo_b200_lattice_star_workspace(nv)
+    if tmp is None or tmp.numel() < ws:
+        tmp = torch.empty(ws, dtype=torch.uint8, device=f.device)
+    _lib.call("shgo_b200_lattice_star", d, gen, _ptr(f), v0, nv, _ptr(is_min), _ptr(tmp), tmp.numel(),
+              _stream())
     return is_min
 
 

@@ -137,7 +137,7 @@ def lattice_coords(d, gen, tab, v0, nv):
     return torch.from_numpy(np.ascontiguousarray(x.T))
 
 
-def lattice_star(d, gen, f, v0=0, nv=None, is_min=None):
+def lattice_star(d, gen, f, v0=0, nv=None, is_min=None, tmp=None):
     out = orc.lattice_star(d, gen, f.numpy())
     nv = len(out) - v0 if nv is None else nv
     return torch.from_numpy(out[v0:v0 + nv].copy())
