@@ -9,7 +9,7 @@ The star test needs neighbours' f across shards.  Two exchanges are implemented:
                LOCAL neighbours (no communication); phase 2 finishes the few rows that survived --
                their remote neighbours' f values are read in place over NVLink by the kernel itself,
                8 bytes per remote neighbour of a candidate.  Collectives are used for plumbing only
-               (two stream-ordered barriers per iteration, pool gather).
+               (one stream-ordered barrier per iteration, pool gather).
   'allgather'  one all_gather of the f vector (NCCL on GPUs; gloo in the CPU tests), then the
                single-GPU star kernel on the rank's rows.  8 n (G-1)/G bytes received per GPU.
 
@@ -115,8 +115,14 @@ class ShardedSobolIteration:
         self.work = hp.PoolWorkspace(self.rows, self.rows if pool_cap is None else pool_cap, dev)
         self._token = torch.zeros(1, dtype=torch.int32, device=dev)
         self.peer = None
+        self.off0 = int(row_ptr_local[0].item())
+        self._k = 0
         if self.exchange == "p2p":
-            self.peer = PeerMappedVector(self.rows, group)
+            # two peer-mapped buffers used alternately: iteration k+1 writes the other buffer while
+            # slow peers may still be reading buffer k, so ONE barrier per iteration is enough
+            # (a rank passes barrier k+1 only after every peer has finished its reads of step k)
+            self.peers = [PeerMappedVector(self.rows, group), PeerMappedVector(self.rows, group)]
+            self.peer = self.peers[0]
             self.f_my = self.peer.local
             self.f_all = None
             ws = _lib.lib().shgo_b200_star_remote_workspace(self.rows, self.rows)
@@ -130,16 +136,23 @@ class ShardedSobolIteration:
         dist.all_reduce(self._token, group=self.group)
 
     def step(self, events=None):
+        """One iteration; free of host synchronisation (capturable in a CUDA graph)."""
+        if self.exchange == "p2p":
+            self.peer = self.peers[self._k & 1]
+            self.f_my = self.peer.local
+            self._k += 1
         hp.eval_sobol(self.functor, self.gset, self.tab, self.row0, self.rows, f=self.f_my, feasible=self.feas)
         if events:
             events[0].record()
         if self.exchange == "p2p":
             # phase 1 needs nobody else; the barrier (every shard of f complete before anyone reads
             # it remotely) is only waited for after it
-            hp.star_csr_local(self.row_ptr, self.col, self.row0, self.f_my, self.feas, self.is_min, self.nfev)
+            hp.star_csr_local(self.row_ptr, self.col, self.row0, self.f_my, self.feas, self.is_min,
+                              self.nfev, self.off0)
             self._barrier()
             hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table, self.peer.own_ptr,
-                               self.world, self.rows, self.rank, self.is_min, self._remote_tmp, self.rows)
+                               self.world, self.rows, self.rank, self.is_min, self._remote_tmp, self.rows,
+                               self.off0)
         else:
             if self.exchange == "allgather":
                 _all_gather(self.f_all, self.f_my, self.group)
@@ -148,12 +161,11 @@ class ShardedSobolIteration:
                 hp.star_csr(self.row_ptr, self.col, f_all, is_min=self.is_min, feasible=self.feas,
                             nfev=self.nfev)
             else:
-                hp.star_csr_shard(self.row_ptr, self.col, self.row0, f_all, self.feas, self.is_min, self.nfev)
+                hp.star_csr_shard(self.row_ptr, self.col, self.row0, f_all, self.feas, self.is_min,
+                                  self.nfev, self.off0)
         if events:
             events[1].record()
         hp.compact_pool(self.is_min, base=self.row0, work=self.work)
-        if self.exchange == "p2p":
-            self._barrier()            # nobody overwrites f while a peer may still be reading it
 
     def local_pool(self):
         c = int(self.work.count[0].item())
@@ -176,5 +188,7 @@ class ShardedSobolIteration:
 
     def close(self):
         if self.peer is not None:
-            self.peer.close()
+            for p in self.peers:
+                p.close()
             self.peer = None
+            self.peers = []

@@ -152,22 +152,24 @@ def star_csr(row_ptr, col, f, row0=0, rows=None, is_min=None, feasible=None, nfe
     return is_min
 
 
-def star_csr_shard(row_ptr_local, col_local, row0, f_all, feasible, is_min, nfev):
+def star_csr_shard(row_ptr_local, col_local, row0, f_all, feasible, is_min, nfev, off0=None):
     """Star test of one GPU's rows against the whole (gathered) f vector.  row_ptr_local is the
     slice row_ptr[row0 : row0+rows+1] (global offsets), col_local the matching slice of col; the C
     ABI addresses the whole graph, so the slices are passed by their virtual bases."""
     rows = row_ptr_local.numel() - 1
-    off0 = int(row_ptr_local[0].item()) if rows >= 0 else 0
+    if off0 is None:     # pass it in to keep the call free of host synchronisation (graph capture)
+        off0 = int(row_ptr_local[0].item())
     _lib.call("shgo_b200_star_csr_nfev", row_ptr_local.data_ptr() - row0 * 8,
               col_local.data_ptr() - off0 * 4, _ptr(f_all), _ptr(feasible), row0, rows,
               col_local.numel(), _ptr(is_min), _ptr(nfev), _stream())
     return is_min
 
 
-def star_csr_local(row_ptr_local, col_local, row0, f_own, feasible, flags, nfev):
+def star_csr_local(row_ptr_local, col_local, row0, f_own, feasible, flags, nfev, off0=None):
     """Multi-GPU phase 1: this GPU's rows against its OWN shard of f; flags 0 / 1 / 2 (candidate)."""
     rows = row_ptr_local.numel() - 1
-    off0 = int(row_ptr_local[0].item())
+    if off0 is None:
+        off0 = int(row_ptr_local[0].item())
     _lib.call("shgo_b200_star_csr_local", row_ptr_local.data_ptr() - row0 * 8,
               col_local.data_ptr() - off0 * 4, _ptr(f_own), _ptr(feasible), row0, rows,
               col_local.numel(), _ptr(flags), _ptr(nfev), _stream())
@@ -175,10 +177,11 @@ def star_csr_local(row_ptr_local, col_local, row0, f_own, feasible, flags, nfev)
 
 
 def star_csr_remote(row_ptr_local, col_local, row0, peer_table, f_own_ptr, nshards, rows_per_shard,
-                    my_shard, flags, tmp, cand_cap):
+                    my_shard, flags, tmp, cand_cap, off0=None):
     """Multi-GPU phase 2: candidates' remote neighbours, f read in place from the peer-mapped shards."""
     rows = row_ptr_local.numel() - 1
-    off0 = int(row_ptr_local[0].item())
+    if off0 is None:
+        off0 = int(row_ptr_local[0].item())
     _lib.call("shgo_b200_star_csr_remote", row_ptr_local.data_ptr() - row0 * 8,
               col_local.data_ptr() - off0 * 4, _ptr(peer_table), f_own_ptr, nshards, rows_per_shard,
               my_shard, rows, _ptr(flags), cand_cap, _ptr(tmp), tmp.numel(), _stream())

@@ -79,7 +79,7 @@ def star_csr(row_ptr, col, f, row0=0, rows=None, is_min=None, feasible=None, nfe
     return torch.from_numpy(out)
 
 
-def star_csr_shard(row_ptr_local, col_local, row0, f_all, feasible, is_min, nfev):
+def star_csr_shard(row_ptr_local, col_local, row0, f_all, feasible, is_min, nfev, off0=None):
     rp = row_ptr_local.numpy()
     rows = len(rp) - 1
     rp0 = rp - rp[0]
