@@ -339,6 +339,14 @@ def main():
         return
 
     hbm_peak, peak_src = peaks()
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_star_traffic.json")
+    if os.path.exists(tp):           # dram bytes of ONE launch from a committed ncu --set full capture
+        with open(tp) as fh:
+            tj = json.load(fh)
+        if tj.get("log2n") == args.log2n and tj.get("n_gpus") == world:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_src = tj["source"]
     nnz_l = rows * m
     alg_bytes = 4 * nnz_l + 17 * rows
     achieved = alg_bytes / (star_ms * 1e-3) / 1e9
@@ -358,7 +366,7 @@ def main():
                                 "none": "none"}[args.exchange if world > 1 else "none"]},
         "roofline": {"bound": "hbm", "kernel": "star_csr_kernel", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": star_ms},
         "eval_kernel": {"ms_per_launch": eval_ms, "tflops_fp64_algorithmic": eval_tflops,
                         "fp64_peak_measured_tflops": fp64_peak,
