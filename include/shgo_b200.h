@@ -152,15 +152,21 @@ SHGO_B200_API int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t 
  *     Rewrites the 2s in flags to 0 / 1.  All ranks must have finished writing f before any rank
  *     starts phase 2 (caller's barrier).  cand_cap: room for candidate indices (rows is always
  *     enough); tmp: shgo_b200_star_remote_workspace(rows, cand_cap) bytes.
+ * Both calls classify a sub-range [row0, row0+rows) of the owned shard [own0, own0+own_rows)
+ * (own0 = my_shard * rows_per_shard), so that a caller can pipeline chunks: phase 2 of one chunk
+ * (NVLink bound) overlaps phase 1 of the next (HBM bound) on another stream.  flags / feasible are
+ * indexed relative to row0, f_own relative to own0.
  * row_ptr / col are this shard's slices addressed with GLOBAL row ids / offsets (virtual bases). */
 SHGO_B200_API int shgo_b200_star_csr_local(const int64_t *row_ptr, const int32_t *col, const double *f_own,
-                             const uint8_t *feasible, uint64_t row0, uint64_t rows,
-                             uint64_t nnz_hint, uint8_t *flags, uint64_t *nfev, void *stream);
+                             const uint8_t *feasible, uint64_t own0, uint64_t own_rows,
+                             uint64_t row0, uint64_t rows, uint64_t nnz_hint, uint8_t *flags,
+                             uint64_t *nfev, void *stream);
 SHGO_B200_API size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap);
 SHGO_B200_API int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col,
                               const double *const *f_shards, const double *f_own, int nshards,
-                              uint64_t rows_per_shard, int my_shard, uint64_t rows, uint8_t *flags,
-                              uint64_t cand_cap, void *tmp, size_t tmp_bytes, void *stream);
+                              uint64_t rows_per_shard, int my_shard, uint64_t row0, uint64_t rows,
+                              uint8_t *flags, uint64_t cand_cap, void *tmp, size_t tmp_bytes,
+                              void *stream);
 /* cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle / cudaFree;
  * handle64 is the 64-byte cudaIpcMemHandle_t to ship to the peer processes. */
 SHGO_B200_API int shgo_b200_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64);

@@ -127,8 +127,8 @@ template <bool LOCAL>
 __global__ void __launch_bounds__(kStarThreads, 5)
 star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                 const double *__restrict__ f, const uint8_t *__restrict__ feasible, uint64_t row0,
-                uint64_t rows, int cap_w, uint8_t *__restrict__ is_min,
-                unsigned long long *__restrict__ nfev)
+                uint64_t rows, uint64_t own0, uint64_t own_rows, int cap_w,
+                uint8_t *__restrict__ is_min, unsigned long long *__restrict__ nfev)
 {
     extern __shared__ __align__(16) int32_t star_smem[];
     const int lane = threadIdx.x & 31;
@@ -136,7 +136,7 @@ star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__
     const uint64_t ntiles = (rows + 31) >> 5;
     const uint64_t gw = ((uint64_t)blockIdx.x * kStarThreads + threadIdx.x) >> 5;
     const uint64_t nw = ((uint64_t)gridDim.x * kStarThreads) >> 5;
-    const double *f_rows = LOCAL ? f - row0 : f;
+    const double *f_rows = LOCAL ? f - own0 : f;  // LOCAL: f is the owned shard, rows own0 .. own0+own_rows
     unsigned present_feasible = 0;
     const uint64_t stream_pol = l2_evict_first_policy(), keep = l2_evict_last_policy();
     // row_ptr / f of the NEXT tile are fetched while the current one is walked
@@ -166,7 +166,7 @@ star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__
             __syncwarp();
             int k = (int)(b - s0a);
             const int le = (int)(e - s0a), last = le - 1;
-            const uint32_t r0 = (uint32_t)row0, nr = (uint32_t)rows;
+            const uint32_t r0 = (uint32_t)own0, nr = (uint32_t)own_rows;
             if (ok) ok = star_round<4, LOCAL>(sc, f, fv, k, last, r0, nr, remote, keep);
             if (ok && k < le) ok = star_round<8, LOCAL>(sc, f, fv, k, last, r0, nr, remote, keep);
             while (ok && k < le) ok = star_round<16, LOCAL>(sc, f, fv, k, last, r0, nr, remote, keep);
@@ -174,8 +174,8 @@ star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__
             for (int64_t k = b; k < e && ok; ++k) {
                 const int32_t w = __ldg(col + k);
                 if (LOCAL) {
-                    const uint32_t l = (uint32_t)w - (uint32_t)row0;
-                    if (l < (uint32_t)rows) ok = fv < ld_nc_f64(f + l); else remote = true;
+                    const uint32_t l = (uint32_t)w - (uint32_t)own0;
+                    if (l < (uint32_t)own_rows) ok = fv < ld_nc_f64(f + l); else remote = true;
                 } else {
                     ok = fv < ld_nc_f64(f + w);
                 }
@@ -213,16 +213,16 @@ struct ShardedF {
 __global__ void __launch_bounds__(256)
 star_remote_kernel(const int64_t *__restrict__ cand, const uint64_t *__restrict__ ncand, uint64_t cap,
                    const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col, ShardedF facc,
-                   const double *__restrict__ f_own, uint64_t row0, uint64_t rows,
+                   const double *__restrict__ f_own, uint64_t own0, uint64_t own_rows, uint64_t row0,
                    uint8_t *__restrict__ is_min)
 {
     uint64_t n = *ncand;
     if (n > cap) n = cap;
     for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n;
          c += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t lr = (uint64_t)cand[c];
+        const uint64_t lr = (uint64_t)cand[c];  // relative to row0 (the classified range)
         const uint64_t r = row0 + lr;
-        const double fv = ld_nc_f64(f_own + lr);
+        const double fv = ld_nc_f64(f_own + (r - own0));
         bool ok = true;
         const int64_t e = row_ptr[r + 1];
         // 8 neighbour ids, then their (remote only) f values, are in flight together: a candidate
@@ -234,7 +234,7 @@ star_remote_kernel(const int64_t *__restrict__ cand, const uint64_t *__restrict_
             for (int u = 0; u < 8; ++u) w[u] = __ldg(col + (k + u < e ? k + u : e - 1));
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                fn[u] = ((uint32_t)w[u] - (uint32_t)row0 < (uint32_t)rows) ? pos_inf() : facc(w[u]);
+                fn[u] = ((uint32_t)w[u] - (uint32_t)own0 < (uint32_t)own_rows) ? pos_inf() : facc(w[u]);
 #pragma unroll
             for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
         }
@@ -609,8 +609,9 @@ static size_t star_smem_bytes(uint64_t rows, uint64_t nnz_hint, long *cap_out)
 
 template <bool LOCAL>
 static int launch_star(const int64_t *row_ptr, const int32_t *col, const double *f,
-                       const uint8_t *feasible, uint64_t row0, uint64_t rows, uint64_t nnz_hint,
-                       uint8_t *is_min, uint64_t *nfev, cudaStream_t st)
+                       const uint8_t *feasible, uint64_t row0, uint64_t rows, uint64_t own0,
+                       uint64_t own_rows, uint64_t nnz_hint, uint8_t *is_min, uint64_t *nfev,
+                       cudaStream_t st)
 {
     if (nfev) SHGO_CUDA_TRY(cudaMemsetAsync(nfev, 0, sizeof(uint64_t), st));
     if (rows == 0) return SHGO_B200_OK;
@@ -627,7 +628,8 @@ static int launch_star(const int64_t *row_ptr, const int32_t *col, const double 
     uint64_t tiles = (rows + kStarThreads - 1) / kStarThreads;
     uint64_t grid = (uint64_t)sm_count() * occ;
     if (grid > tiles) grid = tiles;
-    kern<<<(unsigned)grid, kStarThreads, smem, st>>>(row_ptr, col, f, feasible, row0, rows, (int)cap, is_min,
+    kern<<<(unsigned)grid, kStarThreads, smem, st>>>(row_ptr, col, f, feasible, row0, rows, own0, own_rows,
+                                                    (int)cap, is_min,
                                                     reinterpret_cast<unsigned long long *>(nfev));
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;
@@ -654,7 +656,7 @@ extern "C" {
 int shgo_b200_star_csr(const int64_t *row_ptr, const int32_t *col, const double *f, uint64_t row0,
                        uint64_t rows, uint64_t nnz_hint, uint8_t *is_min, void *stream)
 {
-    return launch_star<false>(row_ptr, col, f, nullptr, row0, rows, nnz_hint, is_min, nullptr,
+    return launch_star<false>(row_ptr, col, f, nullptr, row0, rows, 0, 0, nnz_hint, is_min, nullptr,
                               as_stream(stream));
 }
 
@@ -663,16 +665,18 @@ int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t *col, const do
                             uint8_t *is_min, uint64_t *nfev, void *stream)
 {
     SHGO_REQUIRE(nfev, "null nfev");
-    return launch_star<false>(row_ptr, col, f, feasible, row0, rows, nnz_hint, is_min, nfev, as_stream(stream));
+    return launch_star<false>(row_ptr, col, f, feasible, row0, rows, 0, 0, nnz_hint, is_min, nfev,
+                              as_stream(stream));
 }
 
 int shgo_b200_star_csr_local(const int64_t *row_ptr, const int32_t *col, const double *f_own,
-                             const uint8_t *feasible, uint64_t row0, uint64_t rows, uint64_t nnz_hint,
-                             uint8_t *flags, uint64_t *nfev, void *stream)
+                             const uint8_t *feasible, uint64_t own0, uint64_t own_rows, uint64_t row0,
+                             uint64_t rows, uint64_t nnz_hint, uint8_t *flags, uint64_t *nfev, void *stream)
 {
-    SHGO_REQUIRE(row0 + rows <= 0x7fffffffull, "row range out of int32");
-    return launch_star<true>(row_ptr, col, f_own, feasible, row0, rows, nnz_hint, flags, nfev,
-                             as_stream(stream));
+    SHGO_REQUIRE(own0 + own_rows <= 0x7fffffffull, "row range out of int32");
+    SHGO_REQUIRE(row0 >= own0 && row0 + rows <= own0 + own_rows, "classified rows outside the owned shard");
+    return launch_star<true>(row_ptr, col, f_own, feasible, row0, rows, own0, own_rows, nnz_hint, flags,
+                             nfev, as_stream(stream));
 }
 
 size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap)
@@ -682,15 +686,16 @@ size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap)
 
 int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const double *const *f_shards,
                               const double *f_own, int nshards, uint64_t rows_per_shard, int my_shard,
-                              uint64_t rows, uint8_t *flags, uint64_t cand_cap, void *tmp, size_t tmp_bytes,
-                              void *stream)
+                              uint64_t row0, uint64_t rows, uint8_t *flags, uint64_t cand_cap, void *tmp,
+                              size_t tmp_bytes, void *stream)
 {
     cudaStream_t st = as_stream(stream);
     if (rows == 0) return SHGO_B200_OK;
     SHGO_REQUIRE(row_ptr && f_shards && f_own && flags && tmp, "null pointer");
     SHGO_REQUIRE(nshards >= 1 && my_shard >= 0 && my_shard < nshards, "bad shard index");
-    SHGO_REQUIRE(rows_per_shard >= 1 && rows_per_shard <= 0x7fffffffull && rows <= rows_per_shard,
-                 "bad shard size");
+    SHGO_REQUIRE(rows_per_shard >= 1 && rows_per_shard <= 0x7fffffffull, "bad shard size");
+    const uint64_t own0 = (uint64_t)my_shard * rows_per_shard;
+    SHGO_REQUIRE(row0 >= own0 && row0 + rows <= own0 + rows_per_shard, "classified rows outside the owned shard");
     if (tmp_bytes < shgo_b200_star_remote_workspace(rows, cand_cap))
         return fail(SHGO_B200_ERR_WORKSPACE, "remote-phase workspace: need %zu bytes, got %zu",
                     shgo_b200_star_remote_workspace(rows, cand_cap), tmp_bytes);
@@ -702,10 +707,13 @@ int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const 
     uint64_t *ncand = reinterpret_cast<uint64_t *>(p);
     if (int rc = compact_flags(flags, rows, /*match=*/2, 0, cand, cand_cap, ncand, ctmp, st)) return rc;
     ShardedF facc{f_shards, (uint32_t)rows_per_shard};
-    const uint64_t row0 = (uint64_t)my_shard * rows_per_shard;
     // candidates beyond cand_cap would be left with flag 2; callers size cand_cap = rows to be safe
-    star_remote_kernel<<<sm_count() * 8, 256, 0, st>>>(cand, ncand, cand_cap, row_ptr, col, facc, f_own, row0,
-                                                     rows, flags);
+    uint64_t blocks = (rows / 16 + 255) / 256;  // ~ one thread per expected candidate, capped
+    const uint64_t capb = (uint64_t)sm_count() * 8;
+    if (blocks > capb) blocks = capb;
+    if (blocks < 1) blocks = 1;
+    star_remote_kernel<<<(unsigned)blocks, 256, 0, st>>>(cand, ncand, cand_cap, row_ptr, col, facc, f_own, own0,
+                                                        rows_per_shard, row0, flags);
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;
 }

@@ -98,7 +98,7 @@ class ShardedSobolIteration:
     GLOBAL vertex ids."""
 
     def __init__(self, functor, gset, tab, n, row_ptr_local, col_local, group=None, exchange="p2p",
-                 pool_cap=None):
+                 pool_cap=None, chunks=1):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -127,13 +127,28 @@ class ShardedSobolIteration:
             self.f_all = None
             ws = _lib.lib().shgo_b200_star_remote_workspace(self.rows, self.rows)
             self._remote_tmp = torch.empty(ws, dtype=torch.uint8, device=dev)
+            self._comm = torch.cuda.Stream(device=dev)
+            self._remote = torch.cuda.Stream(device=dev)
+            # chunks > 1 pipelines phase 2 of one chunk under phase 1 of the next on a second stream;
+            # measured on B200 it does not pay (the persistent phase-1 kernel leaves no room for the
+            # phase-2 CTAs to co-run), so the default is a single chunk
+            self.chunks = int(chunks)
+            self._nfev_parts = torch.zeros(self.chunks, dtype=torch.int64, device=dev)
         else:
             self.f_all = torch.empty(n if self.world > 1 else self.rows, dtype=torch.float64, device=dev)
             self.f_my = self.f_all[self.row0:self.row0 + self.rows] if self.world > 1 else self.f_all
 
-    def _barrier(self):
-        # stream-ordered (NCCL all-reduce of one int): no host synchronisation
-        dist.all_reduce(self._token, group=self.group)
+    def _barrier_async(self):
+        """Stream-ordered barrier "every rank has finished writing its f shard", issued on a side
+        stream right after the evaluation so that its latency (and the skew between ranks) hides
+        behind phase 1 of the star test; returns nothing, _barrier_wait() joins it."""
+        main = torch.cuda.current_stream()
+        self._comm.wait_stream(main)
+        with torch.cuda.stream(self._comm):
+            dist.all_reduce(self._token, group=self.group)
+
+    def _barrier_wait(self):
+        torch.cuda.current_stream().wait_stream(self._comm)
 
     def step(self, events=None):
         """One iteration; free of host synchronisation (capturable in a CUDA graph)."""
@@ -145,14 +160,27 @@ class ShardedSobolIteration:
         if events:
             events[0].record()
         if self.exchange == "p2p":
-            # phase 1 needs nobody else; the barrier (every shard of f complete before anyone reads
-            # it remotely) is only waited for after it
-            hp.star_csr_local(self.row_ptr, self.col, self.row0, self.f_my, self.feas, self.is_min,
-                              self.nfev, self.off0)
-            self._barrier()
-            hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table, self.peer.own_ptr,
-                               self.world, self.rows, self.rank, self.is_min, self._remote_tmp, self.rows,
-                               self.off0)
+            # Phase 1 needs nobody else; the barrier (every shard of f complete before anyone reads
+            # it remotely) runs concurrently with it on a side stream.  The rows are classified in
+            # chunks so that phase 2 of a chunk -- bound by the rate of small NVLink reads -- runs on
+            # a second stream underneath phase 1 of the next chunk, which is bound by HBM.
+            self._barrier_async()
+            main = torch.cuda.current_stream()
+            self._remote.wait_stream(self._comm)
+            C = self.chunks
+            per = self.rows // C
+            for c in range(C):
+                r0 = self.row0 + c * per
+                nr = per if c < C - 1 else self.rows - c * per
+                hp.star_csr_local(self.row_ptr, self.col, self.row0, self.f_my, self.feas, self.is_min,
+                                  self._nfev_parts[c:c + 1], self.off0, r0, nr)
+                self._remote.wait_stream(main)
+                with torch.cuda.stream(self._remote):
+                    hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table,
+                                       self.peer.own_ptr, self.world, self.rows, self.rank, self.is_min,
+                                       self._remote_tmp, self.off0, r0, nr)
+            main.wait_stream(self._remote)
+            torch.sum(self._nfev_parts, 0, keepdim=True, out=self.nfev)
         else:
             if self.exchange == "allgather":
                 _all_gather(self.f_all, self.f_my, self.group)

@@ -165,26 +165,35 @@ def star_csr_shard(row_ptr_local, col_local, row0, f_all, feasible, is_min, nfev
     return is_min
 
 
-def star_csr_local(row_ptr_local, col_local, row0, f_own, feasible, flags, nfev, off0=None):
-    """Multi-GPU phase 1: this GPU's rows against its OWN shard of f; flags 0 / 1 / 2 (candidate)."""
-    rows = row_ptr_local.numel() - 1
+def star_csr_local(row_ptr_local, col_local, own0, f_own, feasible, flags, nfev, off0=None, r0=None,
+                   nrows=None):
+    """Multi-GPU phase 1: rows [r0, r0+nrows) of this GPU's shard (default: all of it) against its
+    OWN shard of f; flags 0 / 1 / 2 (candidate).  feasible / flags are whole-shard tensors."""
+    own_rows = row_ptr_local.numel() - 1
     if off0 is None:
         off0 = int(row_ptr_local[0].item())
-    _lib.call("shgo_b200_star_csr_local", row_ptr_local.data_ptr() - row0 * 8,
-              col_local.data_ptr() - off0 * 4, _ptr(f_own), _ptr(feasible), row0, rows,
-              col_local.numel(), _ptr(flags), _ptr(nfev), _stream())
+    r0 = own0 if r0 is None else r0
+    nrows = own_rows if nrows is None else nrows
+    sh = r0 - own0
+    hint = col_local.numel() * nrows // max(own_rows, 1)
+    _lib.call("shgo_b200_star_csr_local", row_ptr_local.data_ptr() - own0 * 8,
+              col_local.data_ptr() - off0 * 4, _ptr(f_own),
+              feasible.data_ptr() + sh if feasible is not None else None, own0, own_rows, r0, nrows, hint,
+              flags.data_ptr() + sh, _ptr(nfev), _stream())
     return flags
 
 
-def star_csr_remote(row_ptr_local, col_local, row0, peer_table, f_own_ptr, nshards, rows_per_shard,
-                    my_shard, flags, tmp, cand_cap, off0=None):
+def star_csr_remote(row_ptr_local, col_local, own0, peer_table, f_own_ptr, nshards, rows_per_shard,
+                    my_shard, flags, tmp, off0=None, r0=None, nrows=None):
     """Multi-GPU phase 2: candidates' remote neighbours, f read in place from the peer-mapped shards."""
-    rows = row_ptr_local.numel() - 1
+    own_rows = row_ptr_local.numel() - 1
     if off0 is None:
         off0 = int(row_ptr_local[0].item())
-    _lib.call("shgo_b200_star_csr_remote", row_ptr_local.data_ptr() - row0 * 8,
+    r0 = own0 if r0 is None else r0
+    nrows = own_rows if nrows is None else nrows
+    _lib.call("shgo_b200_star_csr_remote", row_ptr_local.data_ptr() - own0 * 8,
               col_local.data_ptr() - off0 * 4, _ptr(peer_table), f_own_ptr, nshards, rows_per_shard,
-              my_shard, rows, _ptr(flags), cand_cap, _ptr(tmp), tmp.numel(), _stream())
+              my_shard, r0, nrows, flags.data_ptr() + (r0 - own0), nrows, _ptr(tmp), tmp.numel(), _stream())
     return flags
 
 

@@ -409,13 +409,20 @@ def test_two_phase_sharded_star_emulated_on_one_gpu(hp, nshards):
             flags = torch.empty(rows, dtype=torch.uint8, device="cuda")
             nfev = torch.zeros(1, dtype=torch.int64, device="cuda")
             hp.star_csr_local(rp_l, col_l, row0, f_sh[s], None, flags, nfev)
+            if nshards == 2:       # chunked classification of the same shard gives the same flags
+                fl2 = torch.empty_like(flags)
+                nf2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+                h = rows // 2
+                hp.star_csr_local(rp_l, col_l, row0, f_sh[s], None, fl2, nf2[0:1], None, row0, h)
+                hp.star_csr_local(rp_l, col_l, row0, f_sh[s], None, fl2, nf2[1:2], None, row0 + h, rows - h)
+                assert torch.equal(fl2, flags) and int(nf2.sum().item()) == int(nfev.item())
             fl = flags.cpu().numpy()
             ncand += int((fl == 2).sum())
             # phase-1 flags are already final wherever they are 0, and 1 means "no remote neighbour"
             assert not np.any((fl == 0) & (ref[row0:row0 + rows] == 1))
             ws = __import__("shgo_b200")._lib.lib().shgo_b200_star_remote_workspace(rows, rows)
             tmp = torch.empty(ws, dtype=torch.uint8, device="cuda")
-            hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, flags, tmp, rows)
+            hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, flags, tmp)
             got[row0:row0 + rows] = flags.cpu().numpy()
             assert int(nfev.item()) == int(np.count_nonzero(np.diff(rp_h[row0:row0 + rows + 1]) > 0))
         assert np.array_equal(got, ref), (graph, nshards)
