@@ -73,3 +73,19 @@ def test_registered_numpy_callables_agree_with_oracle_definitions():
     assert F.cattle_feed_g2(x) == orc.np_cattle_g2(x)
     x = rng.uniform(-512, 512, 2)
     assert F.eggholder(x) == orc.np_eggholder(x)
+
+
+def test_near_tie_report():
+    from shgo_b200.ties import explain_pool_difference, ulp_distance
+    # path graph 0-1-2-3; evaluation b perturbs f[1] by one ulp across the tie with f[2]
+    rp = np.array([0, 1, 3, 5, 6]); col = np.array([1, 0, 2, 1, 3, 2])
+    fa = np.array([3.0, 1.0, 1.0, 2.0])
+    fb = fa.copy(); fb[1] = np.nextafter(1.0, 0.0)
+    ma = np.array([0, 0, 0, 0], bool)            # exact tie: neither 1 nor 2 is a strict minimum
+    mb = np.array([0, 1, 0, 0], bool)
+    ok, rep = explain_pool_difference(rp, col, fa, fb, ma, mb)
+    assert ok and rep[0]["vertex"] == 1 and rep[0]["edges"] == [(1, 2)]
+    fb[1] = 0.5                                   # a real difference is not a near-tie
+    ok, rep = explain_pool_difference(rp, col, fa, fb, ma, mb)
+    assert not ok
+    assert ulp_distance(1.0, np.nextafter(1.0, 2.0)) == 1.0
