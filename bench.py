@@ -129,14 +129,17 @@ def reference_arm(args):
     t = times[args.warmup:]
     ms = 1e3 * sum(t) / len(t)
     val = n / (ms * 1e-3)
-    sample = ("oracle C port (oracle/shgo_oracle.c, OpenMP) of the same step on 2^%d points; the "
-              "Python reference itself runs ~1.5e4 points/s (BASELINE.md)" % args.cpu_log2n)
+    sample = ("each step = the same hot path (generate, evaluate, mask, star test, pool) run by the "
+              "oracle C port (oracle/shgo_oracle.c, OpenMP, all host threads) on a bounded sample of "
+              "2^%d points with its degree-%d hypercube graph; the Python reference itself runs "
+              "~1.5e4 points/s single-core (BASELINE.md)" % (args.cpu_log2n, args.cpu_log2n))
     print(json.dumps({
         "impl": "reference", "metric": "sample points evaluated+classified/sec", "value": val,
         "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.cpu_log2n), "points": n},
+        "config": {"workload": workload_name(args.log2n), "points": 1 << args.log2n,
+                   "sample_points_per_step": n},
         "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
