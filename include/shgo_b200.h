@@ -105,7 +105,8 @@ SHGO_B200_API int shgo_b200_mask_infeasible(double *f, uint64_t n, const double 
  * a symmetric CSR with ascending, de-duplicated rows; vertices that never occupy a connecting
  * slot get an empty row (they do not exist in the reference's vertex cache).
  *   simplices [S][dp1] int32;  row_ptr [n+1] int64;  col [col_cap] int32 (6*S always suffices)
- *   nnz       device uint64 receiving the number of directed entries
+ *   nnz       device uint64 receiving the number of directed entries; ~0 (UINT64_MAX) when some
+ *             simplex refers to a vertex outside [0, n) (such edges are dropped)
  *   tmp       workspace; call shgo_b200_csr_workspace() for the size
  */
 SHGO_B200_API size_t shgo_b200_csr_workspace(uint64_t S, int dp1, uint64_t n);

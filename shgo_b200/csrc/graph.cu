@@ -462,6 +462,12 @@ __global__ void first_seen_kernel(const int32_t *__restrict__ simplices, uint64_
     }
 }
 
+// a simplex index outside [0, n) poisons the result: report it through nnz = ~0
+__global__ void flag_bad_kernel(const int *__restrict__ bad, uint64_t *__restrict__ nnz)
+{
+    if (*bad) *nnz = ~0ull;
+}
+
 __global__ void edge_fill_kernel(const unsigned long long *__restrict__ table, uint64_t slots,
                                  const int64_t *__restrict__ row_ptr, uint32_t *__restrict__ cursor,
                                  int32_t *__restrict__ col_tmp)
@@ -827,6 +833,7 @@ int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, 
     if (S > 0) {
         edge_fill_kernel<<<grid_for(slots, 256, 8), 256, 0, st>>>(table, slots, row_ptr, cursor, col_tmp);
         row_sort_kernel<<<grid_for(n * 32, 256, 8), 256, 0, st>>>(row_ptr, n, col_tmp, col);
+        flag_bad_kernel<<<1, 1, 0, st>>>(bad, nnz);
     }
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;

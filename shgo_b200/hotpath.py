@@ -54,12 +54,25 @@ class SobolTables:
             raise ValueError("bounds span not exactly scalable by 2^-30; unsupported")
 
 
+MAX_FUSED_DIM = 32      # kMaxDim of the kernels (tables live in shared memory)
+
+
 def sobol_points(tab, k0, n, layout="soa", out=None):
     """Points k0..k0+n-1 scaled to the bounds, bit-identical to the reference's `self.C`.
 
-    layout 'soa' -> (d, n) coordinate-major; 'aos' -> (n, d) like the reference."""
+    layout 'soa' -> (d, n) coordinate-major; 'aos' -> (n, d) like the reference.  More than 32
+    axes are generated 32 at a time (the direction numbers of an axis do not depend on the others)."""
     d = tab.d
     dev = tab.sv.device
+    if d > MAX_FUSED_DIM:
+        x = torch.empty((d, n), dtype=torch.float64, device=dev)
+        for j0 in range(0, d, MAX_FUSED_DIM):
+            j1 = min(d, j0 + MAX_FUSED_DIM)
+            _lib.call("shgo_b200_sobol_fill", _ptr(tab.sv[j0:j1]), j1 - j0, k0, n, _ptr(tab.lb[j0:j1]),
+                      _ptr(tab.ub[j0:j1]), _ptr(x[j0:j1]), max(n, 1), 0, _stream())
+        if layout == "soa":
+            return x
+        return x.t().contiguous()
     if layout == "soa":
         x = out if out is not None else torch.empty((d, n), dtype=torch.float64, device=dev)
         _lib.call("shgo_b200_sobol_fill", _ptr(tab.sv), d, k0, n, _ptr(tab.lb), _ptr(tab.ub), _ptr(x),
@@ -122,7 +135,10 @@ def csr_from_simplices(simplices, n):
     tmp = torch.empty(ws, dtype=torch.uint8, device=dev)
     _lib.call("shgo_b200_csr_from_simplices", _ptr(simplices), S, dp1, n, _ptr(row_ptr), _ptr(col),
               col.numel(), _ptr(nnz), _ptr(tmp), ws, _stream())
-    return row_ptr, col[: int(nnz.item())]
+    count = int(nnz.item())
+    if count < 0:          # ~0 as int64: the kernel saw a vertex index outside [0, n)
+        raise ValueError("simplices refer to a vertex outside [0, %d)" % n)
+    return row_ptr, col[:count]
 
 
 def first_seen(simplices, n):

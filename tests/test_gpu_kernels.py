@@ -57,6 +57,22 @@ def test_sobol_points_bit_exact(hp, d, k0, n):
     assert np.array_equal(aos, ref)
 
 
+def test_sobol_points_many_axes(hp):
+    """41 axes (reference tests/test__shgo.py:719-728 `test_13_high_sobol`) and 100 axes"""
+    from scipy.stats import qmc
+    for d in (41, 100):
+        tab = hp.SobolTables([(0.0, 1.0)] * d)
+        ref = qmc.Sobol(d=d, scramble=False, seed=0).random(256)
+        assert np.array_equal(hp.sobol_points(tab, 0, 256, "aos").cpu().numpy(), ref)
+        assert np.array_equal(hp.sobol_points(tab, 0, 256, "soa").cpu().numpy().T, ref)
+
+
+def test_csr_rejects_out_of_range_simplices(hp):
+    simp = torch.tensor([[0, 1, 2], [1, 2, 7]], dtype=torch.int32, device="cuda")
+    with pytest.raises(ValueError):
+        hp.csr_from_simplices(simp, 5)
+
+
 def test_sobol_points_match_scipy(hp):
     from scipy.stats import qmc
     d, n = 6, 2048
