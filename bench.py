@@ -194,8 +194,10 @@ def main():
         torch.bitwise_xor(i, bits, out=col_l[s:e])
     col_l = col_l.reshape(-1)
     del bits, i
+    # rows list i ^ 2^j in ascending j, so the neighbours owned by other GPUs (the top log2 N bits)
+    # are the last entries of every row: the remote_at_ends promise of the sharded star test holds
     it = sdist.ShardedSobolIteration(fid, F.G_NONE, tab, n, row_ptr_l, col_l, exchange=args.exchange,
-                                     pool_cap=rows // 8)
+                                     pool_cap=rows // 8, remote_at_ends=True)
     stream = torch.cuda.current_stream()
 
     def step(ev=None):

@@ -151,7 +151,11 @@ SHGO_B200_API int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t 
  *     nshards base pointers, own shard = f_own, others mapped over NVLink with shgo_b200_ipc_*).
  *     Only 8 bytes per remote neighbour of a candidate cross NVLink; there is no exchange of f.
  *     Rewrites the 2s in flags to 0 / 1.  All ranks must have finished writing f before any rank
- *     starts phase 2 (caller's barrier).  cand_cap: room for candidate indices (rows is always
+ *     starts phase 2 (caller's barrier).  remote_at_ends != 0 is the caller's promise that in every
+ *     row the neighbours owned by other GPUs form a prefix and/or a suffix of the row -- true for
+ *     ascending rows (shgo_b200_csr_from_simplices output) because a GPU owns a contiguous id range:
+ *     the remote neighbours of a candidate are then looked up at the two ends of its row instead of
+ *     by walking it.  cand_cap: room for candidate indices (rows is always
  *     enough); tmp: shgo_b200_star_remote_workspace(rows, cand_cap) bytes.
  * Both calls classify a sub-range [row0, row0+rows) of the owned shard [own0, own0+own_rows)
  * (own0 = my_shard * rows_per_shard), so that a caller can pipeline chunks: phase 2 of one chunk
@@ -166,8 +170,8 @@ SHGO_B200_API size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t can
 SHGO_B200_API int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col,
                               const double *const *f_shards, const double *f_own, int nshards,
                               uint64_t rows_per_shard, int my_shard, uint64_t row0, uint64_t rows,
-                              uint8_t *flags, uint64_t cand_cap, void *tmp, size_t tmp_bytes,
-                              void *stream);
+                              int remote_at_ends, uint8_t *flags, uint64_t cand_cap, void *tmp,
+                              size_t tmp_bytes, void *stream);
 /* cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle / cudaFree;
  * handle64 is the 64-byte cudaIpcMemHandle_t to ship to the peer processes. */
 SHGO_B200_API int shgo_b200_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64);

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256)
 star_remote_kernel(const int64_t *__restrict__ cand, const uint64_t *__restrict__ ncand, uint64_t cap,
                    const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col, ShardedF facc,
                    const double *__restrict__ f_own, uint64_t own0, uint64_t own_rows, uint64_t row0,
-                   uint8_t *__restrict__ is_min)
+                   int remote_at_ends, uint8_t *__restrict__ is_min)
 {
     uint64_t n = *ncand;
     if (n > cap) n = cap;
@@ -224,19 +224,56 @@ star_remote_kernel(const int64_t *__restrict__ cand, const uint64_t *__restrict_
         const uint64_t r = row0 + lr;
         const double fv = ld_nc_f64(f_own + (r - own0));
         bool ok = true;
-        const int64_t e = row_ptr[r + 1];
-        // 8 neighbour ids, then their (remote only) f values, are in flight together: a candidate
-        // costs ~2 latency round trips per 8 neighbours instead of one per neighbour
-        for (int64_t k = row_ptr[r]; k < e && ok; k += 8) {
-            int32_t w[8];
-            double fn[8];
+        const int64_t b = row_ptr[r], e = row_ptr[r + 1];
+        const uint32_t o0 = (uint32_t)own0, on = (uint32_t)own_rows;
+        if (remote_at_ends) {
+            // Promise of the caller: the neighbours owned by other GPUs sit at the two ENDS of the
+            // row (e.g. ascending rows: ids below own0 first, ids >= own0+own_rows last).  Read four entries from each end together and
+            // fetch the remote ones' values over NVLink: two latency round trips and two sectors of
+            // `col` per candidate instead of a walk over the whole row.  A side whose four entries
+            // are all remote is continued inwards.
+            int64_t klo = b, khi = e;  // [klo, khi) is what has not been looked at yet
+            bool more_lo = true, more_hi = true;
+            while (ok && klo < khi && (more_lo || more_hi)) {
+                int32_t w[8];
+                bool use[8];
+                double fn[8];
+                const int64_t nlo = more_lo ? min((int64_t)4, khi - klo) : 0;
+                const int64_t nhi = more_hi ? min((int64_t)4, khi - klo - nlo) : 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) w[u] = __ldg(col + (k + u < e ? k + u : e - 1));
+                for (int u = 0; u < 4; ++u) {
+                    w[u] = u < nlo ? __ldg(col + klo + u) : 0;
+                    w[4 + u] = u < nhi ? __ldg(col + khi - 1 - u) : 0;
+                }
+                bool all_lo = nlo == 4, all_hi = nhi == 4;
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                fn[u] = ((uint32_t)w[u] - (uint32_t)own0 < (uint32_t)own_rows) ? pos_inf() : facc(w[u]);
+                for (int u = 0; u < 4; ++u) {
+                    use[u] = u < nlo && ((uint32_t)w[u] - o0 >= on);
+                    use[4 + u] = u < nhi && ((uint32_t)w[4 + u] - o0 >= on);
+                    all_lo = all_lo && (use[u] || u >= nlo);
+                    all_hi = all_hi && (use[4 + u] || u >= nhi);
+                }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
+                for (int u = 0; u < 8; ++u) fn[u] = use[u] ? facc(w[u]) : pos_inf();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
+                klo += nlo;
+                khi -= nhi;
+                more_lo = more_lo && all_lo;
+                more_hi = more_hi && all_hi;
+            }
+        } else {
+            // 8 neighbour ids, then their (remote only) f values, are in flight together
+            for (int64_t k = b; k < e && ok; k += 8) {
+                int32_t w[8];
+                double fn[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = __ldg(col + (k + u < e ? k + u : e - 1));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) fn[u] = ((uint32_t)w[u] - o0 < on) ? pos_inf() : facc(w[u]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
+            }
         }
         is_min[lr] = ok ? 1 : 0;
     }
@@ -692,8 +729,8 @@ size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap)
 
 int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const double *const *f_shards,
                               const double *f_own, int nshards, uint64_t rows_per_shard, int my_shard,
-                              uint64_t row0, uint64_t rows, uint8_t *flags, uint64_t cand_cap, void *tmp,
-                              size_t tmp_bytes, void *stream)
+                              uint64_t row0, uint64_t rows, int remote_at_ends, uint8_t *flags,
+                              uint64_t cand_cap, void *tmp, size_t tmp_bytes, void *stream)
 {
     cudaStream_t st = as_stream(stream);
     if (rows == 0) return SHGO_B200_OK;
@@ -719,7 +756,7 @@ int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const 
     if (blocks > capb) blocks = capb;
     if (blocks < 1) blocks = 1;
     star_remote_kernel<<<(unsigned)blocks, 256, 0, st>>>(cand, ncand, cand_cap, row_ptr, col, facc, f_own, own0,
-                                                        rows_per_shard, row0, flags);
+                                                        rows_per_shard, row0, remote_at_ends, flags);
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;
 }

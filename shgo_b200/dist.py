@@ -98,7 +98,7 @@ class ShardedSobolIteration:
     GLOBAL vertex ids."""
 
     def __init__(self, functor, gset, tab, n, row_ptr_local, col_local, group=None, exchange="p2p",
-                 pool_cap=None, chunks=1):
+                 pool_cap=None, chunks=1, remote_at_ends=False):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -116,6 +116,9 @@ class ShardedSobolIteration:
         self._token = torch.zeros(1, dtype=torch.int32, device=dev)
         self.peer = None
         self.off0 = int(row_ptr_local[0].item())
+        # promise: in every row the neighbours owned by other ranks form a prefix and/or suffix
+        # (true for ascending rows, i.e. for every CSR built by csr_from_simplices)
+        self.remote_at_ends = bool(remote_at_ends)
         self._k = 0
         if self.exchange == "p2p":
             # two peer-mapped buffers used alternately: iteration k+1 writes the other buffer while
@@ -178,7 +181,7 @@ class ShardedSobolIteration:
                 with torch.cuda.stream(self._remote):
                     hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table,
                                        self.peer.own_ptr, self.world, self.rows, self.rank, self.is_min,
-                                       self._remote_tmp, self.off0, r0, nr)
+                                       self._remote_tmp, self.off0, r0, nr, self.remote_at_ends)
             main.wait_stream(self._remote)
             torch.sum(self._nfev_parts, 0, keepdim=True, out=self.nfev)
         else:

@@ -200,8 +200,10 @@ def star_csr_local(row_ptr_local, col_local, own0, f_own, feasible, flags, nfev,
 
 
 def star_csr_remote(row_ptr_local, col_local, own0, peer_table, f_own_ptr, nshards, rows_per_shard,
-                    my_shard, flags, tmp, off0=None, r0=None, nrows=None):
-    """Multi-GPU phase 2: candidates' remote neighbours, f read in place from the peer-mapped shards."""
+                    my_shard, flags, tmp, off0=None, r0=None, nrows=None, remote_at_ends=False):
+    """Multi-GPU phase 2: candidates' remote neighbours, f read in place from the peer-mapped shards.
+    remote_at_ends: promise that remote neighbours form a prefix/suffix of every row (true for
+    ascending rows); enables the two-ends lookup."""
     own_rows = row_ptr_local.numel() - 1
     if off0 is None:
         off0 = int(row_ptr_local[0].item())
@@ -209,7 +211,8 @@ def star_csr_remote(row_ptr_local, col_local, own0, peer_table, f_own_ptr, nshar
     nrows = own_rows if nrows is None else nrows
     _lib.call("shgo_b200_star_csr_remote", row_ptr_local.data_ptr() - own0 * 8,
               col_local.data_ptr() - off0 * 4, _ptr(peer_table), f_own_ptr, nshards, rows_per_shard,
-              my_shard, r0, nrows, flags.data_ptr() + (r0 - own0), nrows, _ptr(tmp), tmp.numel(), _stream())
+              my_shard, r0, nrows, 1 if remote_at_ends else 0, flags.data_ptr() + (r0 - own0), nrows, _ptr(tmp),
+              tmp.numel(), _stream())
     return flags
 
 

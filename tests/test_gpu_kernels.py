@@ -438,7 +438,12 @@ def test_two_phase_sharded_star_emulated_on_one_gpu(hp, nshards):
             assert not np.any((fl == 0) & (ref[row0:row0 + rows] == 1))
             ws = __import__("shgo_b200")._lib.lib().shgo_b200_star_remote_workspace(rows, rows)
             tmp = torch.empty(ws, dtype=torch.uint8, device="cuda")
-            hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, flags, tmp)
+            fl_slow = flags.clone()
+            hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, fl_slow, tmp)
+            # both test graphs keep remote neighbours at the row ends (top bits last / ascending rows)
+            hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, flags, tmp,
+                               remote_at_ends=True)
+            assert torch.equal(flags, fl_slow)
             got[row0:row0 + rows] = flags.cpu().numpy()
             assert int(nfev.item()) == int(np.count_nonzero(np.diff(rp_h[row0:row0 + rows + 1]) > 0))
         assert np.array_equal(got, ref), (graph, nshards)

@@ -29,14 +29,16 @@ rp_l = torch.arange(row0 * m, (row0 + rows + 1) * m, m, dtype=torch.int64, devic
 i = torch.arange(row0, row0 + rows, dtype=torch.int32, device=dev)[:, None]
 col_l = (i ^ (1 << torch.arange(m, dtype=torch.int32, device=dev))[None, :]).reshape(-1)
 res = {}
-for ex in ("p2p", "allgather"):
-    it = sd.ShardedSobolIteration(F.F_RASTRIGIN, F.G_NONE, tab, n, rp_l, col_l, exchange=ex)
+for ex in ("p2p", "allgather", "p2p-walk"):
+    it = sd.ShardedSobolIteration(F.F_RASTRIGIN, F.G_NONE, tab, n, rp_l, col_l, exchange=ex.split("-")[0],
+                                  remote_at_ends=(ex == "p2p"))
     for _ in range(3):
         it.step()
     torch.cuda.synchronize()
     res[ex] = (it.global_pool(), it.global_nfev())
     it.close()
 ok = np.array_equal(res["p2p"][0], res["allgather"][0]) and res["p2p"][1] == res["allgather"][1]
+ok = ok and np.array_equal(res["p2p"][0], res["p2p-walk"][0])
 if rank == 0:
     rp, col = hp.hypercube_csr(n, dev)
     f, feas = hp.eval_sobol(F.F_RASTRIGIN, F.G_NONE, tab, 0, n)

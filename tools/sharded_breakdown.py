@@ -16,7 +16,8 @@ for s in range(0, rows, 1 << 22):
     e = min(rows, s + (1 << 22))
     torch.bitwise_xor(torch.arange(row0 + s, row0 + e, dtype=torch.int32, device=dev)[:, None], bits, out=col_l[s:e])
 col_l = col_l.reshape(-1)
-it = sd.ShardedSobolIteration(F.F_STYBLINSKI_TANG, 0, tab, n, rp_l, col_l, exchange="p2p", pool_cap=rows // 8)
+it = sd.ShardedSobolIteration(F.F_STYBLINSKI_TANG, 0, tab, n, rp_l, col_l, exchange="p2p", pool_cap=rows // 8,
+                              remote_at_ends=True)
 for _ in range(5): it.step()
 torch.cuda.synchronize(); dist.barrier()
 names = ["eval", "local star", "barrier wait", "candidates+remote", "pool compaction"]
@@ -34,7 +35,7 @@ for _ in range(K):
     it._barrier_wait()
     ev[3].record()
     hp.star_csr_remote(it.row_ptr, it.col, it.row0, it.peer.table, it.peer.own_ptr, it.world, it.rows, it.rank,
-                       it.is_min, it._remote_tmp, it.off0)
+                       it.is_min, it._remote_tmp, it.off0, remote_at_ends=True)
     ev[4].record()
     hp.compact_pool(it.is_min, base=it.row0, work=it.work)
     ev[5].record()
