@@ -157,6 +157,9 @@ SHGO_B200_API int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t 
  *     the remote neighbours of a candidate are then looked up at the two ends of its row instead of
  *     by walking it.  cand_cap: room for candidate indices (rows is always
  *     enough); tmp: shgo_b200_star_remote_workspace(rows, cand_cap) bytes.
+ * cand_ws (optional, shgo_b200_star_local_workspace(rows) bytes): phase 1 lists its candidates there
+ * (dense per-warp segments) and phase 2, given the same pointer, consumes the list directly; with
+ * cand_ws == NULL phase 2 compacts the flags itself (tmp / cand_cap).
  * Both calls classify a sub-range [row0, row0+rows) of the owned shard [own0, own0+own_rows)
  * (own0 = my_shard * rows_per_shard), so that a caller can pipeline chunks: phase 2 of one chunk
  * (NVLink bound) overlaps phase 1 of the next (HBM bound) on another stream.  flags / feasible are
@@ -165,13 +168,14 @@ SHGO_B200_API int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t 
 SHGO_B200_API int shgo_b200_star_csr_local(const int64_t *row_ptr, const int32_t *col, const double *f_own,
                              const uint8_t *feasible, uint64_t own0, uint64_t own_rows,
                              uint64_t row0, uint64_t rows, uint64_t nnz_hint, uint8_t *flags,
-                             uint64_t *nfev, void *stream);
+                             void *cand_ws, size_t cand_ws_bytes, uint64_t *nfev, void *stream);
+SHGO_B200_API size_t shgo_b200_star_local_workspace(uint64_t rows);
 SHGO_B200_API size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap);
 SHGO_B200_API int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col,
                               const double *const *f_shards, const double *f_own, int nshards,
                               uint64_t rows_per_shard, int my_shard, uint64_t row0, uint64_t rows,
-                              int remote_at_ends, uint8_t *flags, uint64_t cand_cap, void *tmp,
-                              size_t tmp_bytes, void *stream);
+                              int remote_at_ends, uint8_t *flags, const void *cand_ws,
+                              uint64_t cand_cap, void *tmp, size_t tmp_bytes, void *stream);
 /* cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle / cudaFree;
  * handle64 is the 64-byte cudaIpcMemHandle_t to ship to the peer processes. */
 SHGO_B200_API int shgo_b200_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64);

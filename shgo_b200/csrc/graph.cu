@@ -28,6 +28,7 @@ namespace shgo_b200 {
 // =============================================================================================
 constexpr int kStarWarps = 8;
 constexpr int kStarThreads = kStarWarps * 32;
+constexpr int kMaxStarWarps = 16384;  // upper bound on the warps of one star_csr_kernel launch
 
 // L2 policies: `col` and `row_ptr` are read exactly once -> evict_first, so that the 126 MB L2 is
 // spent on the f values the gathers come back for instead of on the 30 GB stream passing through.
@@ -128,7 +129,8 @@ __global__ void __launch_bounds__(kStarThreads, 5)
 star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                 const double *__restrict__ f, const uint8_t *__restrict__ feasible, uint64_t row0,
                 uint64_t rows, uint64_t own0, uint64_t own_rows, int cap_w,
-                uint8_t *__restrict__ is_min, unsigned long long *__restrict__ nfev)
+                uint8_t *__restrict__ is_min, uint32_t *__restrict__ cand_ws,
+                unsigned long long *__restrict__ nfev)
 {
     extern __shared__ __align__(16) int32_t star_smem[];
     const int lane = threadIdx.x & 31;
@@ -138,6 +140,12 @@ star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__
     const uint64_t nw = ((uint64_t)gridDim.x * kStarThreads) >> 5;
     const double *f_rows = LOCAL ? f - own0 : f;  // LOCAL: f is the owned shard, rows own0 .. own0+own_rows
     unsigned present_feasible = 0;
+    // LOCAL: every warp appends its candidates (flag 2) to a private, dense segment of cand_ws, so
+    // that phase 2 needs no compaction pass: [0] = warps, [1] = segment capacity, [2..2+kMaxStarWarps)
+    // = per-warp counts, then the segments
+    const uint32_t seg_cap = (uint32_t)(((ntiles + nw - 1) / nw) << 5);
+    uint32_t *seg = (LOCAL && cand_ws) ? cand_ws + 2 + kMaxStarWarps + gw * (uint64_t)seg_cap : nullptr;
+    uint32_t ncand = 0;
     const uint64_t stream_pol = l2_evict_first_policy(), keep = l2_evict_last_policy();
     // row_ptr / f of the NEXT tile are fetched while the current one is walked
     StarMeta cur = star_meta(row_ptr, f_rows, row0, rows, gw, ntiles, lane, stream_pol, keep);
@@ -181,8 +189,21 @@ star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__
                 }
             }
         }
-        if (valid) is_min[lr] = ok ? (LOCAL && remote ? 2 : 1) : 0;
+        const bool candidate = LOCAL && valid && ok && remote;
+        if (valid) is_min[lr] = ok ? (candidate ? 2 : 1) : 0;
+        if (LOCAL && seg != nullptr) {
+            const unsigned m = __ballot_sync(0xffffffffu, candidate);
+            if (candidate) seg[ncand + __popc(m & ((1u << lane) - 1u))] = (uint32_t)lr;
+            ncand += __popc(m);
+        }
         __syncwarp();  // the slice is rewritten by the next tile
+    }
+    if (LOCAL && seg != nullptr && lane == 0) {
+        cand_ws[2 + gw] = ncand;
+        if (gw == 0) {
+            cand_ws[0] = (uint32_t)nw;
+            cand_ws[1] = seg_cap;
+        }
     }
     if (nfev != nullptr) {
 #pragma unroll
@@ -210,6 +231,70 @@ struct ShardedF {
     }
 };
 
+__device__ __forceinline__ void star_remote_one(uint64_t lr, const int64_t *__restrict__ row_ptr,
+                                                const int32_t *__restrict__ col, const ShardedF &facc,
+                                                const double *__restrict__ f_own, uint64_t own0,
+                                                uint64_t own_rows, uint64_t row0, int remote_at_ends,
+                                                uint8_t *__restrict__ is_min)
+{
+    const uint64_t r = row0 + lr;
+    const double fv = ld_nc_f64(f_own + (r - own0));
+    bool ok = true;
+    const int64_t b = row_ptr[r], e = row_ptr[r + 1];
+    const uint32_t o0 = (uint32_t)own0, on = (uint32_t)own_rows;
+    if (remote_at_ends) {
+        // Promise of the caller: the neighbours owned by other GPUs sit at the two ENDS of the
+        // row (e.g. ascending rows: ids below own0 first, ids >= own0+own_rows last).  Read four entries from each end together and
+        // fetch the remote ones' values over NVLink: two latency round trips and two sectors of
+        // `col` per candidate instead of a walk over the whole row.  A side whose four entries
+        // are all remote is continued inwards.
+        int64_t klo = b, khi = e;  // [klo, khi) is what has not been looked at yet
+        bool more_lo = true, more_hi = true;
+        while (ok && klo < khi && (more_lo || more_hi)) {
+            int32_t w[8];
+            bool use[8];
+            double fn[8];
+            const int64_t nlo = more_lo ? min((int64_t)4, khi - klo) : 0;
+            const int64_t nhi = more_hi ? min((int64_t)4, khi - klo - nlo) : 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                w[u] = u < nlo ? __ldg(col + klo + u) : 0;
+                w[4 + u] = u < nhi ? __ldg(col + khi - 1 - u) : 0;
+            }
+            bool all_lo = nlo == 4, all_hi = nhi == 4;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                use[u] = u < nlo && ((uint32_t)w[u] - o0 >= on);
+                use[4 + u] = u < nhi && ((uint32_t)w[4 + u] - o0 >= on);
+                all_lo = all_lo && (use[u] || u >= nlo);
+                all_hi = all_hi && (use[4 + u] || u >= nhi);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) fn[u] = use[u] ? facc(w[u]) : pos_inf();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
+            klo += nlo;
+            khi -= nhi;
+            more_lo = more_lo && all_lo;
+            more_hi = more_hi && all_hi;
+        }
+    } else {
+        // 8 neighbour ids, then their (remote only) f values, are in flight together
+        for (int64_t k = b; k < e && ok; k += 8) {
+            int32_t w[8];
+            double fn[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = __ldg(col + (k + u < e ? k + u : e - 1));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) fn[u] = ((uint32_t)w[u] - o0 < on) ? pos_inf() : facc(w[u]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
+        }
+    }
+    is_min[lr] = ok ? 1 : 0;
+}
+
+// candidates from a compacted index list (phase 1 ran without a candidate workspace)
 __global__ void __launch_bounds__(256)
 star_remote_kernel(const int64_t *__restrict__ cand, const uint64_t *__restrict__ ncand, uint64_t cap,
                    const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col, ShardedF facc,
@@ -219,63 +304,27 @@ star_remote_kernel(const int64_t *__restrict__ cand, const uint64_t *__restrict_
     uint64_t n = *ncand;
     if (n > cap) n = cap;
     for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n;
-         c += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t lr = (uint64_t)cand[c];  // relative to row0 (the classified range)
-        const uint64_t r = row0 + lr;
-        const double fv = ld_nc_f64(f_own + (r - own0));
-        bool ok = true;
-        const int64_t b = row_ptr[r], e = row_ptr[r + 1];
-        const uint32_t o0 = (uint32_t)own0, on = (uint32_t)own_rows;
-        if (remote_at_ends) {
-            // Promise of the caller: the neighbours owned by other GPUs sit at the two ENDS of the
-            // row (e.g. ascending rows: ids below own0 first, ids >= own0+own_rows last).  Read four entries from each end together and
-            // fetch the remote ones' values over NVLink: two latency round trips and two sectors of
-            // `col` per candidate instead of a walk over the whole row.  A side whose four entries
-            // are all remote is continued inwards.
-            int64_t klo = b, khi = e;  // [klo, khi) is what has not been looked at yet
-            bool more_lo = true, more_hi = true;
-            while (ok && klo < khi && (more_lo || more_hi)) {
-                int32_t w[8];
-                bool use[8];
-                double fn[8];
-                const int64_t nlo = more_lo ? min((int64_t)4, khi - klo) : 0;
-                const int64_t nhi = more_hi ? min((int64_t)4, khi - klo - nlo) : 0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    w[u] = u < nlo ? __ldg(col + klo + u) : 0;
-                    w[4 + u] = u < nhi ? __ldg(col + khi - 1 - u) : 0;
-                }
-                bool all_lo = nlo == 4, all_hi = nhi == 4;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    use[u] = u < nlo && ((uint32_t)w[u] - o0 >= on);
-                    use[4 + u] = u < nhi && ((uint32_t)w[4 + u] - o0 >= on);
-                    all_lo = all_lo && (use[u] || u >= nlo);
-                    all_hi = all_hi && (use[4 + u] || u >= nhi);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) fn[u] = use[u] ? facc(w[u]) : pos_inf();
-#pragma unroll
-                for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
-                klo += nlo;
-                khi -= nhi;
-                more_lo = more_lo && all_lo;
-                more_hi = more_hi && all_hi;
-            }
-        } else {
-            // 8 neighbour ids, then their (remote only) f values, are in flight together
-            for (int64_t k = b; k < e && ok; k += 8) {
-                int32_t w[8];
-                double fn[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) w[u] = __ldg(col + (k + u < e ? k + u : e - 1));
-#pragma unroll
-                for (int u = 0; u < 8; ++u) fn[u] = ((uint32_t)w[u] - o0 < on) ? pos_inf() : facc(w[u]);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
-            }
-        }
-        is_min[lr] = ok ? 1 : 0;
+         c += (uint64_t)gridDim.x * blockDim.x)
+        star_remote_one((uint64_t)cand[c], row_ptr, col, facc, f_own, own0, own_rows, row0, remote_at_ends,
+                        is_min);
+}
+
+// candidates from the per-warp segments phase 1 wrote: no compaction pass in between
+__global__ void __launch_bounds__(256)
+star_remote_seg_kernel(const uint32_t *__restrict__ cand_ws, const int64_t *__restrict__ row_ptr,
+                       const int32_t *__restrict__ col, ShardedF facc, const double *__restrict__ f_own,
+                       uint64_t own0, uint64_t own_rows, uint64_t row0, int remote_at_ends,
+                       uint8_t *__restrict__ is_min)
+{
+    const uint32_t nw = cand_ws[0], seg_cap = cand_ws[1];
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t sw = gw; sw < nw; sw += tw) {
+        const uint32_t n = cand_ws[2 + sw];
+        const uint32_t *seg = cand_ws + 2 + kMaxStarWarps + sw * (uint64_t)seg_cap;
+        for (uint32_t i = lane; i < n; i += 32)
+            star_remote_one((uint64_t)seg[i], row_ptr, col, facc, f_own, own0, own_rows, row0, remote_at_ends,
+                            is_min);
     }
 }
 
@@ -653,8 +702,8 @@ static size_t star_smem_bytes(uint64_t rows, uint64_t nnz_hint, long *cap_out)
 template <bool LOCAL>
 static int launch_star(const int64_t *row_ptr, const int32_t *col, const double *f,
                        const uint8_t *feasible, uint64_t row0, uint64_t rows, uint64_t own0,
-                       uint64_t own_rows, uint64_t nnz_hint, uint8_t *is_min, uint64_t *nfev,
-                       cudaStream_t st)
+                       uint64_t own_rows, uint64_t nnz_hint, uint8_t *is_min, uint32_t *cand_ws,
+                       uint64_t *nfev, cudaStream_t st)
 {
     if (nfev) SHGO_CUDA_TRY(cudaMemsetAsync(nfev, 0, sizeof(uint64_t), st));
     if (rows == 0) return SHGO_B200_OK;
@@ -671,8 +720,9 @@ static int launch_star(const int64_t *row_ptr, const int32_t *col, const double 
     uint64_t tiles = (rows + kStarThreads - 1) / kStarThreads;
     uint64_t grid = (uint64_t)sm_count() * occ;
     if (grid > tiles) grid = tiles;
+    if (grid * kStarWarps > (uint64_t)kMaxStarWarps) grid = kMaxStarWarps / kStarWarps;
     kern<<<(unsigned)grid, kStarThreads, smem, st>>>(row_ptr, col, f, feasible, row0, rows, own0, own_rows,
-                                                    (int)cap, is_min,
+                                                    (int)cap, is_min, cand_ws,
                                                     reinterpret_cast<unsigned long long *>(nfev));
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;
@@ -699,7 +749,7 @@ extern "C" {
 int shgo_b200_star_csr(const int64_t *row_ptr, const int32_t *col, const double *f, uint64_t row0,
                        uint64_t rows, uint64_t nnz_hint, uint8_t *is_min, void *stream)
 {
-    return launch_star<false>(row_ptr, col, f, nullptr, row0, rows, 0, 0, nnz_hint, is_min, nullptr,
+    return launch_star<false>(row_ptr, col, f, nullptr, row0, rows, 0, 0, nnz_hint, is_min, nullptr, nullptr,
                               as_stream(stream));
 }
 
@@ -708,18 +758,28 @@ int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t *col, const do
                             uint8_t *is_min, uint64_t *nfev, void *stream)
 {
     SHGO_REQUIRE(nfev, "null nfev");
-    return launch_star<false>(row_ptr, col, f, feasible, row0, rows, 0, 0, nnz_hint, is_min, nfev,
+    return launch_star<false>(row_ptr, col, f, feasible, row0, rows, 0, 0, nnz_hint, is_min, nullptr, nfev,
                               as_stream(stream));
 }
 
 int shgo_b200_star_csr_local(const int64_t *row_ptr, const int32_t *col, const double *f_own,
                              const uint8_t *feasible, uint64_t own0, uint64_t own_rows, uint64_t row0,
-                             uint64_t rows, uint64_t nnz_hint, uint8_t *flags, uint64_t *nfev, void *stream)
+                             uint64_t rows, uint64_t nnz_hint, uint8_t *flags, void *cand_ws,
+                             size_t cand_ws_bytes, uint64_t *nfev, void *stream)
 {
     SHGO_REQUIRE(own0 + own_rows <= 0x7fffffffull, "row range out of int32");
     SHGO_REQUIRE(row0 >= own0 && row0 + rows <= own0 + own_rows, "classified rows outside the owned shard");
+    if (cand_ws && cand_ws_bytes < shgo_b200_star_local_workspace(rows))
+        return fail(SHGO_B200_ERR_WORKSPACE, "candidate workspace: need %zu bytes, got %zu",
+                    shgo_b200_star_local_workspace(rows), cand_ws_bytes);
     return launch_star<true>(row_ptr, col, f_own, feasible, row0, rows, own0, own_rows, nnz_hint, flags,
-                             nfev, as_stream(stream));
+                             static_cast<uint32_t *>(cand_ws), nfev, as_stream(stream));
+}
+
+size_t shgo_b200_star_local_workspace(uint64_t rows)
+{
+    // header + per-warp counts + per-warp segments (each rounded up to whole tiles of 32 rows)
+    return align256((2 + (size_t)kMaxStarWarps + rows + 32ull * kMaxStarWarps) * sizeof(uint32_t));
 }
 
 size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap)
@@ -730,15 +790,24 @@ size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap)
 int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const double *const *f_shards,
                               const double *f_own, int nshards, uint64_t rows_per_shard, int my_shard,
                               uint64_t row0, uint64_t rows, int remote_at_ends, uint8_t *flags,
-                              uint64_t cand_cap, void *tmp, size_t tmp_bytes, void *stream)
+                              const void *cand_ws, uint64_t cand_cap, void *tmp, size_t tmp_bytes,
+                              void *stream)
 {
     cudaStream_t st = as_stream(stream);
     if (rows == 0) return SHGO_B200_OK;
-    SHGO_REQUIRE(row_ptr && f_shards && f_own && flags && tmp, "null pointer");
+    SHGO_REQUIRE(row_ptr && f_shards && f_own && flags && (tmp || cand_ws), "null pointer");
     SHGO_REQUIRE(nshards >= 1 && my_shard >= 0 && my_shard < nshards, "bad shard index");
     SHGO_REQUIRE(rows_per_shard >= 1 && rows_per_shard <= 0x7fffffffull, "bad shard size");
     const uint64_t own0 = (uint64_t)my_shard * rows_per_shard;
     SHGO_REQUIRE(row0 >= own0 && row0 + rows <= own0 + rows_per_shard, "classified rows outside the owned shard");
+    if (cand_ws) {  // phase 1 already listed the candidates
+        ShardedF fa{f_shards, (uint32_t)rows_per_shard};
+        star_remote_seg_kernel<<<sm_count() * 8, 256, 0, st>>>(static_cast<const uint32_t *>(cand_ws), row_ptr, col,
+                                                             fa, f_own, own0, rows_per_shard, row0,
+                                                             remote_at_ends, flags);
+        SHGO_CUDA_TRY(cudaGetLastError());
+        return SHGO_B200_OK;
+    }
     if (tmp_bytes < shgo_b200_star_remote_workspace(rows, cand_cap))
         return fail(SHGO_B200_ERR_WORKSPACE, "remote-phase workspace: need %zu bytes, got %zu",
                     shgo_b200_star_remote_workspace(rows, cand_cap), tmp_bytes);

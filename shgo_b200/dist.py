@@ -130,6 +130,9 @@ class ShardedSobolIteration:
             self.f_all = None
             ws = _lib.lib().shgo_b200_star_remote_workspace(self.rows, self.rows)
             self._remote_tmp = torch.empty(ws, dtype=torch.uint8, device=dev)
+            # phase 1 lists its candidates here, phase 2 consumes the list (no compaction pass)
+            self._cand_ws = torch.empty(_lib.lib().shgo_b200_star_local_workspace(self.rows),
+                                        dtype=torch.uint8, device=dev)
             self._comm = torch.cuda.Stream(device=dev)
             self._remote = torch.cuda.Stream(device=dev)
             # chunks > 1 pipelines phase 2 of one chunk under phase 1 of the next on a second stream;
@@ -176,12 +179,13 @@ class ShardedSobolIteration:
                 r0 = self.row0 + c * per
                 nr = per if c < C - 1 else self.rows - c * per
                 hp.star_csr_local(self.row_ptr, self.col, self.row0, self.f_my, self.feas, self.is_min,
-                                  self._nfev_parts[c:c + 1], self.off0, r0, nr)
+                                  self._nfev_parts[c:c + 1], self.off0, r0, nr, self._cand_ws)
                 self._remote.wait_stream(main)
                 with torch.cuda.stream(self._remote):
                     hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table,
                                        self.peer.own_ptr, self.world, self.rows, self.rank, self.is_min,
-                                       self._remote_tmp, self.off0, r0, nr, self.remote_at_ends)
+                                       self._remote_tmp, self.off0, r0, nr, self.remote_at_ends,
+                                       self._cand_ws)
             main.wait_stream(self._remote)
             torch.sum(self._nfev_parts, 0, keepdim=True, out=self.nfev)
         else:

@@ -182,7 +182,7 @@ def star_csr_shard(row_ptr_local, col_local, row0, f_all, feasible, is_min, nfev
 
 
 def star_csr_local(row_ptr_local, col_local, own0, f_own, feasible, flags, nfev, off0=None, r0=None,
-                   nrows=None):
+                   nrows=None, cand_ws=None):
     """Multi-GPU phase 1: rows [r0, r0+nrows) of this GPU's shard (default: all of it) against its
     OWN shard of f; flags 0 / 1 / 2 (candidate).  feasible / flags are whole-shard tensors."""
     own_rows = row_ptr_local.numel() - 1
@@ -195,12 +195,14 @@ def star_csr_local(row_ptr_local, col_local, own0, f_own, feasible, flags, nfev,
     _lib.call("shgo_b200_star_csr_local", row_ptr_local.data_ptr() - own0 * 8,
               col_local.data_ptr() - off0 * 4, _ptr(f_own),
               feasible.data_ptr() + sh if feasible is not None else None, own0, own_rows, r0, nrows, hint,
-              flags.data_ptr() + sh, _ptr(nfev), _stream())
+              flags.data_ptr() + sh, _ptr(cand_ws), cand_ws.numel() if cand_ws is not None else 0, _ptr(nfev),
+              _stream())
     return flags
 
 
 def star_csr_remote(row_ptr_local, col_local, own0, peer_table, f_own_ptr, nshards, rows_per_shard,
-                    my_shard, flags, tmp, off0=None, r0=None, nrows=None, remote_at_ends=False):
+                    my_shard, flags, tmp, off0=None, r0=None, nrows=None, remote_at_ends=False,
+                    cand_ws=None):
     """Multi-GPU phase 2: candidates' remote neighbours, f read in place from the peer-mapped shards.
     remote_at_ends: promise that remote neighbours form a prefix/suffix of every row (true for
     ascending rows); enables the two-ends lookup."""
@@ -211,8 +213,8 @@ def star_csr_remote(row_ptr_local, col_local, own0, peer_table, f_own_ptr, nshar
     nrows = own_rows if nrows is None else nrows
     _lib.call("shgo_b200_star_csr_remote", row_ptr_local.data_ptr() - own0 * 8,
               col_local.data_ptr() - off0 * 4, _ptr(peer_table), f_own_ptr, nshards, rows_per_shard,
-              my_shard, r0, nrows, 1 if remote_at_ends else 0, flags.data_ptr() + (r0 - own0), nrows, _ptr(tmp),
-              tmp.numel(), _stream())
+              my_shard, r0, nrows, 1 if remote_at_ends else 0, flags.data_ptr() + (r0 - own0), _ptr(cand_ws),
+              nrows, _ptr(tmp), tmp.numel() if tmp is not None else 0, _stream())
     return flags
 
 

@@ -444,6 +444,14 @@ def test_two_phase_sharded_star_emulated_on_one_gpu(hp, nshards):
             hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, flags, tmp,
                                remote_at_ends=True)
             assert torch.equal(flags, fl_slow)
+            # phase 1 listing its candidates itself, phase 2 consuming that list
+            from shgo_b200 import _lib as L
+            cws = torch.empty(L.lib().shgo_b200_star_local_workspace(rows), dtype=torch.uint8, device="cuda")
+            fl3 = torch.empty_like(flags)
+            hp.star_csr_local(rp_l, col_l, row0, f_sh[s], None, fl3, nfev, cand_ws=cws)
+            hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, fl3, None,
+                               remote_at_ends=True, cand_ws=cws)
+            assert torch.equal(fl3, flags)
             got[row0:row0 + rows] = flags.cpu().numpy()
             assert int(nfev.item()) == int(np.count_nonzero(np.diff(rp_h[row0:row0 + rows + 1]) > 0))
         assert np.array_equal(got, ref), (graph, nshards)
