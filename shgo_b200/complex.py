@@ -322,7 +322,8 @@ class DeviceComplex:
         n = pts.shape[0]
         simp = simp.astype(np.int32, copy=False)
         # vertices are keyed by coordinate tuple in the reference: coincident points are ONE vertex
-        canon = self._coincident_map(pts)
+        # (points of the unscrambled Sobol sequence are pairwise distinct: no need to look)
+        canon = None if self._sampler_tables_if_points_are_sobol(pts) is not None else self._coincident_map(pts)
         if canon is not None:
             simp = canon[simp].astype(np.int32)
         simp_d = torch.from_numpy(np.ascontiguousarray(simp)).to(self.device)

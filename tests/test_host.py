@@ -89,3 +89,27 @@ def test_near_tie_report():
     ok, rep = explain_pool_difference(rp, col, fa, fb, ma, mb)
     assert not ok
     assert ulp_distance(1.0, np.nextafter(1.0, 2.0)) == 1.0
+
+
+def test_lattice_host_mirror_matches_oracle():
+    """shgo_b200.lattice (coordinate tables, id <-> lattice index, neighbour enumeration used to
+    materialise stars) against the oracle's closed form."""
+    from oracle import oracle as orc
+    from shgo_b200 import lattice
+    for bounds, gen in [([(0, 1.0)] * 3, 2), ([(-5.12, 5.12)] * 4, 1), ([(-32.768, 32.768)] * 2, 3),
+                        ([(0.0, 2.0)] * 5, 1), ([(-1.0, 6.0)], 3)]:
+        d = len(bounds)
+        assert np.array_equal(lattice.coordinate_tables(bounds, gen), orc.lattice_tables(bounds, gen))
+        nv, ng = lattice.counts(d, gen)
+        assert (nv, ng) == orc.lattice_nvert(d, gen)
+        tab = lattice.coordinate_tables(bounds, gen)
+        p = lattice.decode(np.arange(nv), d, gen)
+        x = np.stack([tab[i][p[:, i]] for i in range(d)], 1)
+        assert np.array_equal(x, orc.lattice_coords(bounds, gen))
+        rp, col = orc.lattice_csr(d, gen)
+        for v in range(0, nv, max(1, nv // 50)):
+            assert sorted(lattice.neighbours(v, d, gen).tolist()) == col[rp[v]:rp[v + 1]].tolist()
+        assert np.array_equal(lattice.vertex_ids(p[:ng] // 2, d, gen, True), np.arange(ng))
+        assert np.array_equal(lattice.vertex_ids(p[ng:] // 2, d, gen, False), np.arange(ng, nv))
+    with pytest.raises(lattice.LatticeArtefactError):
+        lattice.coordinate_tables([(-3.3, 7.1)], 2)

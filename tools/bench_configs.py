@@ -75,6 +75,40 @@ def csr_build(d, log2n):
         d, log2n, len(tri.simplices), t_qhull, n, len(tri.simplices) / t * 1e3, t, col.numel()))
 
 
+def hot_path_in_driver(name, fn, bounds, n):
+    """The hot path as the driver sees it (everything of iterate_delaunay after qhull + minimizers):
+    vf_to_vv + process_pools + minimizers on the SAME simplices, Python Complex vs DeviceComplex."""
+    m = api.driver_module()
+    times = {}
+    for label in ("python", "device"):
+        if label == "device":
+            s_ = shgo_b200.SHGO(fn, bounds, n=n, iters=1, sampling_method="sobol")
+        else:
+            api.uninstall()
+            s_ = m.SHGO(fn, bounds, n=n, iters=1, sampling_method="sobol")
+        s_.nc += s_.n
+        s_.sampled_surface(infty_cons_sampl=s_.infty_cons_sampl)
+        s_.delaunay_triangulation(n_prc=0)
+        best = None
+        for rep in range(2 if label == "device" else 1):
+            if rep:       # fresh complex for the repeat (first device pass pays cudaMalloc / module load)
+                s_.HC = type(s_.HC)(dim=s_.dim, domain=s_.bounds, sfield=s_.func, constraints=s_.constraints)
+                s_.HC._sampler = getattr(s_, "_b200_sampler", None)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s_.HC.vf_to_vv(s_.Tri.points, s_.Tri.simplices)
+            s_.HC.V.process_pools()
+            s_.minimizers()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        times[label] = (best, len(s_.minimizer_pool), s_.HC.V.nfev, len(s_.Tri.simplices))
+    api.uninstall()
+    (tp, pp, nfp, S), (td, pd, nfd, _) = times["python"], times["device"]
+    rows.append("| driver hot path (vf_to_vv + process_pools + minimizers) %s | %d pts, %d simplices | Python Complex %.3f s | DeviceComplex %.4f s | - | x%.0f | pool %d/%d, nfev %d/%d |" % (
+        name, n, S, tp, td, tp / td, pp, pd, nfp, nfd))
+
+
 def whole_call(name, fn, bounds, **kw):
     m = api.driver_module()
     t0 = time.perf_counter()
@@ -91,6 +125,12 @@ def whole_call(name, fn, bounds, **kw):
 
 
 ONLY = os.environ.get("ONLY", "")
+if ONLY == "driver":
+    hot_path_in_driver("Eggholder 2-D", F.eggholder, [(-512, 512)] * 2, 1 << 16)
+    hot_path_in_driver("Rastrigin 3-D", F.rastrigin, [(-5.12, 5.12)] * 3, 1 << 14)
+    hot_path_in_driver("Rastrigin 5-D", F.rastrigin, [(-5.12, 5.12)] * 5, 1 << 10)
+    print("\n".join(rows))
+    sys.exit(0)
 if ONLY == "lattice":
     for g in (0, 1, 2):
         lattice_cfg(10, g, F.F_ACKLEY, [(-32.768, 32.768)] * 10)
@@ -107,6 +147,9 @@ for g in (0, 1, 2):
 csr_build(2, 18)
 csr_build(3, 15)
 csr_build(4, 12)
+hot_path_in_driver("Eggholder 2-D", F.eggholder, [(-512, 512)] * 2, 1 << 16)
+hot_path_in_driver("Rastrigin 3-D", F.rastrigin, [(-5.12, 5.12)] * 3, 1 << 14)
+hot_path_in_driver("Rastrigin 5-D", F.rastrigin, [(-5.12, 5.12)] * 5, 1 << 10)
 whole_call("Eggholder 2-D, sobol n=2^14", F.eggholder, [(-512, 512)] * 2, n=1 << 14, sampling_method="sobol")
 whole_call("Rastrigin 3-D, sobol n=2^12", F.rastrigin, [(-5.12, 5.12)] * 3, n=1 << 12, sampling_method="sobol")
 whole_call("Ackley 4-D, simplicial n=None iters=3", F.ackley, [(-32.768, 32.768)] * 4, n=None, iters=3)
