@@ -106,6 +106,7 @@ class ClockSampler:
 def cpu_run(log2n, repeats):
     import numpy as np
     from oracle import oracle as orc
+    orc.set_threads(os.cpu_count() or 1)     # all host threads, also under torchrun (OMP_NUM_THREADS=1)
     n = 1 << log2n
     b = np.array(BOUNDS)
     sv = orc.sobol_dirnums(D)
@@ -157,7 +158,6 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     from shgo_b200 import functors as F
@@ -245,7 +245,6 @@ def main():
     pc = torch.tensor([int(it.work.count[0].item()), int(it.nfev.item())], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(pc)
-    pool_cap_local = it.work.cap
 
     # eval kernel alone (for the FP64 side of the roofline)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -332,8 +331,10 @@ def main():
         d2h = 16 + int(cnt.value) * 8
         e2e = {"value": ne / wall, "unit": "points/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "points": ne, "ms_per_step": wall * 1e3,
-               "note": "host CSR (pinned) uploaded, pool indices read back, every step; C-ABI "
-                       "shgo_b200_iterate_sobol_host at N=1"}
+               "note": "host CSR (pinned) uploaded, pool indices read back, every step; "
+                       + ("C-ABI shgo_b200_iterate_sobol_host" if world == 1 else
+                          "every rank uploads its CSR shard over its own PCIe link, f exchanged with "
+                          "an NCCL all_gather")}
         if world == 1:
             _lib.lib().shgo_b200_ctx_destroy(ctx)
 

@@ -50,6 +50,7 @@ def lib():
         c = ctypes
         vp = c.c_void_p
         L.oracle_num_threads.restype = c.c_int
+        L.oracle_set_num_threads.argtypes = [c.c_int]
         L.oracle_sobol_dirnums.argtypes = [c.c_int, vp, vp, vp, vp]
         L.oracle_sobol_points.argtypes = [vp, c.c_int, c.c_uint64, c.c_uint64, vp, vp, vp]
         L.oracle_eval.argtypes = [c.c_int, c.c_int, c.c_int, c.c_uint64, vp, vp, vp]
@@ -83,6 +84,11 @@ def _p(a):
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def set_threads(n):
+    """Use n OpenMP threads regardless of OMP_NUM_THREADS (torchrun sets it to 1)."""
+    lib().oracle_set_num_threads(int(n))
 
 
 # ---------------------------------------------------------------------------------------

@@ -41,6 +41,16 @@
 
 #define SOBOL_BITS 30
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline is meant to use the host */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -1,5 +1,4 @@
 """CPU-side checks of the product's host logic (no GPU, no compute calls)."""
-import ctypes
 import os
 import re
 

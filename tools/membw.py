@@ -1,5 +1,5 @@
 """Read-only / copy bandwidth reference on this GPU (torch kernels), to calibrate the HBM ceiling."""
-import torch, time
+import torch
 x = torch.empty(1 << 30, dtype=torch.float64, device="cuda").normal_()   # 8 GiB
 y = torch.empty_like(x)
 def t(fn, n=5):
