@@ -223,6 +223,20 @@ SHGO_B200_API size_t shgo_b200_lattice_star_workspace(uint64_t nv);
 SHGO_B200_API int shgo_b200_lattice_star(int d, int gen, const double *f, uint64_t v0, uint64_t nv,
                            uint8_t *is_min, void *tmp, size_t tmp_bytes, void *stream);
 
+/* ---- local bounds of pool vertices -------------------------------------
+ * Replaces SHGO.construct_lcb_simplicial, shgo/_shgo.py:1246-1270: per pool vertex and axis, the
+ * neighbour coordinate nearest below (lo) / above (hi) the vertex's own, the global bound lb / ub
+ * where there is none.  lo, hi: row-major [m][d]; pool: m vertex ids.
+ *   _csr     explicit graph, coordinates SoA [d][ld] (as shgo_b200_eval_points takes them)
+ *   lattice  whole-generation hypercube complex (closed form on the coordinate table `tab`)
+ */
+SHGO_B200_API int shgo_b200_local_bounds_csr(const int64_t *row_ptr, const int32_t *col, const double *x_soa,
+                               uint64_t ld, int d, const int64_t *pool, uint64_t m, const double *lb,
+                               const double *ub, double *lo, double *hi, void *stream);
+SHGO_B200_API int shgo_b200_lattice_local_bounds(int d, int gen, const double *tab, const int64_t *pool,
+                                   uint64_t m, const double *lb, const double *ub, double *lo, double *hi,
+                                   void *stream);
+
 /* ---- host-buffer convenience path (what bench.py's `e2e` times) ---------------------------------
  * One shgo iteration of the Sobol path with HOST inputs and outputs: uploads the CSR (pinned or
  * pageable host memory), generates + evaluates + masks on the device, classifies, compacts and

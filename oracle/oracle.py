@@ -67,6 +67,7 @@ def lib():
         L.oracle_argmin.restype = c.c_int64
         L.oracle_nfev.argtypes = [vp, vp, c.c_uint64]
         L.oracle_nfev.restype = c.c_uint64
+        L.oracle_local_bounds_csr.argtypes = [vp, vp, vp, c.c_int, vp, c.c_uint64, vp, vp, vp, vp]
         L.oracle_lattice_table.argtypes = [c.c_double, c.c_double, c.c_int, vp]
         L.oracle_lattice_nvert.argtypes = [c.c_int, c.c_int, vp]
         L.oracle_lattice_nvert.restype = c.c_uint64
@@ -279,6 +280,31 @@ def argmin(f, present=None):
 
 def nfev(row_ptr, feas):
     return int(lib().oracle_nfev(_p(row_ptr), _p(feas), len(row_ptr) - 1))
+
+
+def local_bounds_csr(row_ptr, col, x, pool, bounds):
+    """construct_lcb_simplicial of the vertices `pool`; x row-major (n,d).  -> lo, hi (m,d)."""
+    x = np.ascontiguousarray(x, np.float64)
+    d = x.shape[1]
+    pool = np.ascontiguousarray(pool, np.int64)
+    col = np.ascontiguousarray(col, np.int32)
+    b = np.asarray(bounds, np.float64).reshape(d, 2)
+    lb, ub = np.ascontiguousarray(b[:, 0]), np.ascontiguousarray(b[:, 1])
+    lo = np.empty((len(pool), d))
+    hi = np.empty((len(pool), d))
+    lib().oracle_local_bounds_csr(_p(row_ptr), _p(col), _p(x), d, _p(pool), len(pool), _p(lb), _p(ub),
+                                  _p(lo), _p(hi))
+    return lo, hi
+
+
+def csr_from_edges(edges, n):
+    """Symmetric CSR (ascending rows) of an undirected edge list."""
+    e = np.asarray(edges, np.int64).reshape(-1, 2)
+    both = np.concatenate([e, e[:, ::-1]])
+    both = both[np.lexsort((both[:, 1], both[:, 0]))]
+    row_ptr = np.zeros(n + 1, np.int64)
+    np.add.at(row_ptr, both[:, 0] + 1, 1)
+    return np.cumsum(row_ptr), both[:, 1].astype(np.int32)
 
 
 def hypercube_csr(n):

@@ -495,6 +495,31 @@ uint64_t oracle_nfev(const int64_t *row_ptr, const uint8_t *feas, uint64_t n)
     return c;
 }
 
+/* f2. local bounds of a pool vertex, SHGO.construct_lcb_simplicial (_shgo.py:1246-1270):      */
+/* per axis the neighbour coordinate nearest below / above the vertex's own, starting from   */
+/* the global bounds.  x is row-major [n][d]; lo / hi are [m][d].                            */
+void oracle_local_bounds_csr(const int64_t *row_ptr, const int32_t *col, const double *x, int d,
+                             const int64_t *pool, uint64_t m, const double *lb, const double *ub,
+                             double *lo, double *hi)
+{
+    for (uint64_t q = 0; q < m; ++q) {
+        const int64_t v = pool[q];
+        double *l = lo + q * (uint64_t)d, *h = hi + q * (uint64_t)d;
+        for (int i = 0; i < d; ++i) {
+            l[i] = lb[i];
+            h[i] = ub[i];
+        }
+        for (int64_t k = row_ptr[v]; k < row_ptr[v + 1]; ++k) {
+            const double *xn = x + (uint64_t)col[k] * (uint64_t)d;
+            for (int i = 0; i < d; ++i) {
+                const double xi = xn[i], xv = x[(uint64_t)v * (uint64_t)d + i];
+                if (xi < xv && xi > l[i]) l[i] = xi;
+                if (xi > xv && xi < h[i]) h[i] = xi;
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* a8/a9. whole-generation simplicial complex, closed form (verified */
 /* there against Complex.triangulate/refine_all, _complex.py:192-472,514-976)             */

@@ -41,6 +41,8 @@ SIGNATURES = {
     "shgo_b200_lattice_coords": (_i, [_i, _i, _vp, _u64, _u64, _vp, _u64, _vp]),
     "shgo_b200_lattice_star_workspace": (_sz, [_u64]),
     "shgo_b200_lattice_star": (_i, [_i, _i, _vp, _u64, _u64, _vp, _vp, _sz, _vp]),
+    "shgo_b200_local_bounds_csr": (_i, [_vp, _vp, _vp, _u64, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "shgo_b200_lattice_local_bounds": (_i, [_i, _i, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "shgo_b200_ctx_create": (_i, [_i, _vp]),
     "shgo_b200_ctx_destroy": (None, [_vp]),
     "shgo_b200_iterate_sobol_host": (_i, [_vp, _i, _i, _i, _u64, _u64, _vp, _vp, _vp, _vp, _vp,

@@ -47,6 +47,24 @@ def install(driver=None):
         m._shgo_b200_saved_complex = m.Complex
         m.Complex = _cx.DeviceComplex
     _cx.DeviceComplex.scipy_constraint_rule = m.__name__.startswith("scipy.")
+    # local bounds of a pool vertex (construct_lcb_simplicial, _shgo.py:1246-1270) come from the
+    # device when the complex is a DeviceComplex: no neighbour objects are created
+    if not hasattr(m.SHGO, "_shgo_b200_saved_lcb"):
+        saved = m.SHGO.construct_lcb_simplicial
+
+        def construct_lcb_simplicial(self, v_min):
+            if isinstance(self.HC, _cx.DeviceComplex):
+                cbounds = self.HC.local_bounds(v_min, self.bounds)
+                if self.disp:
+                    import logging
+                    logging.info(f'cbounds found for v_min.x_a = {v_min.x_a}')
+                    logging.info(f'cbounds = {cbounds}')
+                return cbounds
+            return saved(self, v_min)
+
+        construct_lcb_simplicial.__doc__ = saved.__doc__
+        m.SHGO._shgo_b200_saved_lcb = saved
+        m.SHGO.construct_lcb_simplicial = construct_lcb_simplicial
     return m
 
 
@@ -56,6 +74,9 @@ def uninstall(driver=None):
     if saved is not None:
         m.Complex = saved
         del m._shgo_b200_saved_complex
+    if hasattr(m.SHGO, "_shgo_b200_saved_lcb"):
+        m.SHGO.construct_lcb_simplicial = m.SHGO._shgo_b200_saved_lcb
+        del m.SHGO._shgo_b200_saved_lcb
     return m
 
 

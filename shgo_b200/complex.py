@@ -279,6 +279,8 @@ class DeviceComplex:
         self._sampler = None
         self._ref = None             # driver-side Python Complex used as a graph generator
         self._ref_keys = []
+        self._lcb, self._lcb_key, self._x_soa = {}, None, None
+        self._epoch = 0              # classifications done so far
         self.argmin_index = -1
         self.pool_indices = np.zeros(0, np.int64)
 
@@ -349,6 +351,7 @@ class DeviceComplex:
         self._row_ptr, self._col = hp.csr_from_simplices(simp_d, n)
         self._row_ptr_host = self._col_host = None
         self._points_host = pts
+        self._x_soa = None
         self._n = n
         self._dirty = True
 
@@ -487,6 +490,7 @@ class DeviceComplex:
     # ---- shared tail: pool, arg-min, materialisation of what the driver will look at ----------
     def _finish_classification(self, present):
         V = self.V
+        self._epoch += 1
         idx, cnt = hp.compact_pool(self._is_min)
         pool = idx[: int(cnt.item())].cpu().numpy()
         # the star() self-loop quirk: a vertex that was a local-search start is
@@ -555,6 +559,37 @@ class DeviceComplex:
             return None
         self._materialise(np.array([vid], np.int64), listed=False)
         return self.V._by_index.get(vid)
+
+    # ---- local bounds (SHGO.construct_lcb_simplicial, _shgo.py:1246-1270) ----------------------
+    def local_bounds(self, v_min, bounds=None):
+        """Box of the local minimisation started at `v_min`: per axis the neighbour coordinates
+        nearest below / above its own, the global bound where there is none -- in the reference's
+        format [[lo, hi], ...].  The boxes of the whole pool are computed by one kernel launch the
+        first time one of them is asked for; no neighbour is materialised on the host."""
+        if self._dirty or self._f is None:
+            raise RuntimeError("local_bounds() before process_pools()")
+        index = int(v_min.index)
+        if index < 0 or self.V._by_index.get(index) is not v_min:
+            raise KeyError("%r is not a vertex of the current complex" % (v_min,))
+        bkey = tuple(map(tuple, np.asarray(self.bounds if bounds is None else bounds, float).reshape(-1, 2)))
+        if self._lcb_key != (self._epoch, bkey):
+            self._lcb, self._lcb_key = {}, (self._epoch, bkey)
+        hit = self._lcb.get(index)
+        if hit is None:
+            ids = np.union1d(self.pool_indices, [index]).astype(np.int64)
+            ids = ids[[i not in self._lcb for i in ids.tolist()]]
+            pool = torch.from_numpy(ids).to(self.device)
+            if self.mode == "lattice":
+                lo, hi = hp.lattice_local_bounds(self.dim, self._lat_gen, self._tab, pool, bkey)
+            else:
+                if self._x_soa is None or self._x_soa.shape[1] != self._n:
+                    self._x_soa = torch.from_numpy(self._points_host).to(self.device).t().contiguous()
+                lo, hi = hp.local_bounds_csr(self._row_ptr, self._col, self._x_soa, pool, bkey)
+            lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+            for k, i in enumerate(ids.tolist()):
+                self._lcb[i] = (lo[k], hi[k])
+            hit = self._lcb[index]
+        return [[float(a), float(b)] for a, b in zip(hit[0], hit[1])]
 
     def _neighbour_ids(self, index):
         if self.mode == "lattice":
@@ -628,6 +663,7 @@ class DeviceComplex:
                 col[rp[i]:rp[i + 1]] = sorted(index[w.x] for w in v.nn)
         col = col[: int(rp[-1])]
         self._points_host = np.array(keys, np.float64).reshape(n, self.dim)
+        self._x_soa = None
         self._row_ptr_host, self._col_host = rp, col
         self._row_ptr = torch.from_numpy(rp).to(self.device)
         colp = np.zeros(max(len(col), 4), np.int32)

@@ -303,6 +303,39 @@ def lattice_star(d, gen, f, v0=0, nv=None, is_min=None, tmp=None):
     return is_min
 
 
+# ---- local bounds of pool vertices ------------------------------------
+def _bounds_vectors(bounds, d, dev):
+    b = torch.as_tensor(np.asarray(bounds, np.float64).reshape(d, 2), device=dev)
+    return b[:, 0].contiguous(), b[:, 1].contiguous()
+
+
+def local_bounds_csr(row_ptr, col, x_soa, pool, bounds):
+    """construct_lcb_simplicial (_shgo.py:1246-1270) of the vertices `pool` of an explicit graph;
+    x_soa is (d, ld) coordinate-major.  -> lo, hi of shape (m, d)."""
+    d, ld = x_soa.shape
+    dev = x_soa.device
+    pool = pool.to(device=dev, dtype=torch.int64).contiguous()
+    m = pool.numel()
+    lb, ub = _bounds_vectors(bounds, d, dev)
+    lo = torch.empty((m, d), dtype=torch.float64, device=dev)
+    hi = torch.empty((m, d), dtype=torch.float64, device=dev)
+    _lib.call("shgo_b200_local_bounds_csr", _ptr(row_ptr), _ptr(col), _ptr(x_soa), ld, d, _ptr(pool), m,
+              _ptr(lb), _ptr(ub), _ptr(lo), _ptr(hi), _stream())
+    return lo, hi
+
+
+def lattice_local_bounds(d, gen, tab, pool, bounds):
+    dev = tab.device
+    pool = pool.to(device=dev, dtype=torch.int64).contiguous()
+    m = pool.numel()
+    lb, ub = _bounds_vectors(bounds, d, dev)
+    lo = torch.empty((m, d), dtype=torch.float64, device=dev)
+    hi = torch.empty((m, d), dtype=torch.float64, device=dev)
+    _lib.call("shgo_b200_lattice_local_bounds", d, gen, _ptr(tab), _ptr(pool), m, _ptr(lb), _ptr(ub),
+              _ptr(lo), _ptr(hi), _stream())
+    return lo, hi
+
+
 def fp64_peak_tflops(iters=4096, repeats=5):
     """Measured FP64 DFMA throughput of the current device (TFLOP/s)."""
     _require_cuda()

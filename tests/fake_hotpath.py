@@ -143,12 +143,26 @@ def lattice_star(d, gen, f, v0=0, nv=None, is_min=None, tmp=None):
     return torch.from_numpy(out[v0:v0 + nv].copy())
 
 
+def local_bounds_csr(row_ptr, col, x_soa, pool, bounds):
+    x = np.ascontiguousarray(x_soa.numpy().T)
+    lo, hi = orc.local_bounds_csr(row_ptr.numpy(), col.numpy(), x, pool.numpy(), bounds)
+    return torch.from_numpy(lo), torch.from_numpy(hi)
+
+
+def lattice_local_bounds(d, gen, tab, pool, bounds):
+    """independent of the product's closed form: walks the oracle's explicit lattice adjacency"""
+    x = orc.lattice_coords(_bounds_from_tab(tab), gen)
+    rp, col = orc.lattice_csr(d, gen)
+    lo, hi = orc.local_bounds_csr(rp, col, x, pool.numpy(), bounds)
+    return torch.from_numpy(lo), torch.from_numpy(hi)
+
+
 def install(monkeypatch):
     """Patch shgo_b200.hotpath in place (functions are looked up as attributes at call time)."""
     from shgo_b200 import hotpath as hp
     for name in ("SobolTables", "sobol_points", "eval_sobol", "eval_points", "mask_infeasible",
                  "csr_from_simplices", "first_seen", "star_csr", "star_csr_shard", "PoolWorkspace", "compact_pool", "argmin", "lattice_eval",
-                 "lattice_coords", "lattice_star"):
+                 "lattice_coords", "lattice_star", "local_bounds_csr", "lattice_local_bounds"):
         monkeypatch.setattr(hp, name, globals()[name])
     monkeypatch.setattr(hp, "_require_cuda", lambda: None)
     monkeypatch.setattr(hp, "_dev", lambda device=None: CPU)

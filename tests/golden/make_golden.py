@@ -126,6 +126,63 @@ def simplicial_pools_case(name, functor, gset, bounds, iters):
                         bounds=np.array(bounds, float), iters=iters, **rec)
 
 
+def _lcb_of(HC, bounds):
+    """construct_lcb_simplicial (_shgo.py:1246-1278) of EVERY vertex of HC, through the
+    reference's own method (unbound call on a stand-in carrying the two attributes it reads)."""
+    class _Self:
+        pass
+    me = _Self()
+    me.bounds, me.disp = bounds, False
+    keys = list(HC.V.cache.keys())
+    idx = {k: i for i, k in enumerate(keys)}
+    lo = np.empty((len(keys), len(bounds)))
+    hi = np.empty((len(keys), len(bounds)))
+    for k, v in HC.V.cache.items():
+        cb = SHGO.construct_lcb_simplicial(me, v)
+        lo[idx[k]] = [c[0] for c in cb]
+        hi[idx[k]] = [c[1] for c in cb]
+    edges = sorted({(min(idx[k], idx[w.x]), max(idx[k], idx[w.x]))
+                    for k, v in HC.V.cache.items() for w in v.nn})
+    return (np.array(keys, float).reshape(len(keys), len(bounds)),
+            small_int(np.array(edges).reshape(-1, 2)), lo, hi)
+
+
+def local_bounds_cases():
+    """local bounds of every vertex, for whole generations of the
+    hypercube complex, a partial refine(n) state and a Delaunay mesh."""
+    out = {}
+    names = []
+
+    def put(name, bounds, HC):
+        x, e, lo, hi = _lcb_of(HC, bounds)
+        out[name + "_bounds"] = np.array(bounds, float)
+        out[name + "_x"], out[name + "_edges"] = x, e
+        out[name + "_lo"], out[name + "_hi"] = lo, hi
+        names.append(name)
+        print(f"local_bounds {name}: |V|={len(x)} |E|={len(e)}")
+
+    for name, bounds, gens in (("lat2d", [(0.0, 1.0)] * 2, 3),
+                               ("lat3d_mixed", [(-3.3, 7.1), (0.0, 2.0), (-5.0, 5.0)], 2),
+                               ("lat4d", [(-5.12, 5.12)] * 4, 1)):
+        HC = Complex(len(bounds), domain=bounds, sfield=lambda x: 0.0)
+        HC.triangulate()
+        for g in range(gens + 1):
+            if g:
+                HC.refine_all()
+            put(f"{name}_g{g}", bounds, HC)
+    bounds = [(-1.0, 2.0)] * 3
+    HC = Complex(3, domain=bounds, sfield=lambda x: 0.0)
+    HC.refine(9)
+    HC.refine(17)
+    HC.refine(30)
+    put("partial3d", bounds, HC)
+    bounds = [(-5.12, 5.12)] * 3
+    s = SHGO(orc.np_rastrigin, bounds, n=256, iters=1, sampling_method="sobol")
+    s.iterate_complex()
+    put("mesh3d", bounds, s.HC)
+    np.savez_compressed(os.path.join(HERE, "local_bounds.npz"), names=np.array(names), **out)
+
+
 def end_to_end():
     out = {}
     r = shgo(rosen, [(0, 2)] * 5)
@@ -143,6 +200,9 @@ def end_to_end():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["local_bounds"]:      # fixtures are independent: regenerate just this one
+        local_bounds_cases()
+        sys.exit(0)
     B512 = [(-5.12, 5.12)]
     sobol_case("sobol_rastrigin_6d_256", "rastrigin", None, B512 * 6, 256, full_simplices=False)
     sobol_case("sobol_rastrigin_3d_4096", "rastrigin", None, B512 * 3, 4096)
@@ -173,3 +233,4 @@ if __name__ == "__main__":
     simplicial_pools_case("simplicial_sphere_2d_cons_it3", "sphere", "sum_le_6",
                           [(-1, 6)] * 2, 3)
     end_to_end()
+    local_bounds_cases()

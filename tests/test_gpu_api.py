@@ -135,3 +135,24 @@ def test_lattice_artefact_bounds_refused(sb):
     from shgo_b200 import functors as F
     with pytest.raises(LatticeArtefactError):
         sb.shgo(F.sphere, [(-3.3, 7.1)] * 3, n=None, iters=2)
+
+
+@pytest.mark.parametrize("kw", [dict(n=None, iters=3), dict(n=30, iters=3), dict(n=70, iters=2)])
+def test_local_bounds_through_the_driver_seam(sb, kw):
+    """SHGO.construct_lcb_simplicial served by the device kernels: identical
+    boxes (lattice closed form for whole generations, CSR walk for partial ones), no neighbour
+    objects created."""
+    from shgo_b200 import api, functors as F
+    s = sb.SHGO(F.styblinski_tang, [(-5.0, 4.0)] * 3, sampling_method="simplicial", **kw)
+    try:
+        s.iterate_complex()
+        s.iterate_complex()
+        s.minimizers()
+        reference_method = api.driver_module().SHGO._shgo_b200_saved_lcb
+        assert len(s.minimizer_pool) > 0
+        boxes = [s.construct_lcb_simplicial(v) for v in s.minimizer_pool]
+        assert len(s.HC.V._unlisted) == 0
+        for v, got in zip(s.minimizer_pool, boxes):
+            assert got == reference_method(s, v)
+    finally:
+        api.uninstall()

@@ -508,3 +508,65 @@ def test_baseline_configs_at_full_size(hp, functor, gset, bounds, log2n):
         fd = hp.eval_sobol(fid, gid, tab, 0, m)[0].cpu().numpy()
         explained, report = explain_pool_difference(rp_h, col_h, fd, fo, sub, ref, max_ulps=8)
         assert explained, report[:5]
+
+
+# ------------------------------------------------------------------------------------------
+# local bounds of pool vertices (construct_lcb_simplicial, _shgo.py:1246-1270)
+def _local_bounds_names():
+    return [str(s) for s in load_golden("local_bounds")["names"]]
+
+
+@pytest.mark.parametrize("name", _local_bounds_names())
+def test_local_bounds_csr_golden(hp, name):
+    """explicit graph: every vertex of every fixture, bit-equal to the reference's own method"""
+    g = load_golden("local_bounds")
+    x, edges, bounds = g[name + "_x"], g[name + "_edges"], g[name + "_bounds"]
+    n = len(x)
+    rp, col = orc.csr_from_edges(edges, n)
+    xs = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    pool = torch.arange(n, dtype=torch.int64).cuda()
+    lo, hi = hp.local_bounds_csr(torch.from_numpy(rp).cuda(), torch.from_numpy(col).cuda(), xs, pool, bounds)
+    assert np.array_equal(lo.cpu().numpy(), g[name + "_lo"])
+    assert np.array_equal(hi.cpu().numpy(), g[name + "_hi"])
+    # a sub-pool in arbitrary order, with repeats
+    sub = np.random.default_rng(3).integers(0, n, 17)
+    lo, hi = hp.local_bounds_csr(torch.from_numpy(rp).cuda(), torch.from_numpy(col).cuda(), xs,
+                                 torch.from_numpy(sub).cuda(), bounds)
+    assert np.array_equal(lo.cpu().numpy(), g[name + "_lo"][sub])
+    assert np.array_equal(hi.cpu().numpy(), g[name + "_hi"][sub])
+
+
+@pytest.mark.parametrize("name", [n for n in _local_bounds_names() if n.startswith(("lat2d", "lat4d"))])
+def test_lattice_local_bounds_golden(hp, name):
+    """whole generations: closed form on the coordinate table == the reference walking v.nn"""
+    from shgo_b200 import lattice
+    g = load_golden("local_bounds")
+    x, bounds = g[name + "_x"], [tuple(b) for b in g[name + "_bounds"]]
+    d, gen = len(bounds), int(name.rsplit("_g", 1)[1])
+    tab = torch.from_numpy(lattice.coordinate_tables(bounds, gen)).cuda()
+    nv, _ = orc.lattice_nvert(d, gen)
+    assert nv == len(x)
+    mine = hp.lattice_coords(d, gen, tab, 0, nv).cpu().numpy().T
+    where = {tuple(c): i for i, c in enumerate(x)}
+    order = np.array([where[tuple(c)] for c in mine])       # golden row of lattice id i
+    lo, hi = hp.lattice_local_bounds(d, gen, tab, torch.arange(nv, dtype=torch.int64).cuda(), bounds)
+    assert np.array_equal(lo.cpu().numpy(), g[name + "_lo"][order])
+    assert np.array_equal(hi.cpu().numpy(), g[name + "_hi"][order])
+
+
+def test_lattice_local_bounds_vs_explicit_walk_10d(hp):
+    """10-D generation 1 (60 073 vertices, stars of up to 59 048): closed form == oracle walk"""
+    d, gen = 10, 1
+    bounds = [(-32.768, 32.768)] * d
+    from shgo_b200 import lattice
+    tab_h = lattice.coordinate_tables(bounds, gen)
+    nv, _ = orc.lattice_nvert(d, gen)
+    pool = np.random.default_rng(5).integers(0, nv, 300)
+    pool[:3] = [0, nv - 1, nv // 2]
+    x = orc.lattice_coords(bounds, gen)
+    rp, col = orc.lattice_csr(d, gen)
+    want_lo, want_hi = orc.local_bounds_csr(rp, col, x, pool, bounds)
+    lo, hi = hp.lattice_local_bounds(d, gen, torch.from_numpy(tab_h).cuda(), torch.from_numpy(pool).cuda(), bounds)
+    assert np.array_equal(lo.cpu().numpy(), want_lo) and np.array_equal(hi.cpu().numpy(), want_hi)
+    assert hp.lattice_local_bounds(d, gen, torch.from_numpy(tab_h).cuda(),
+                                   torch.zeros(0, dtype=torch.int64).cuda(), bounds)[0].shape == (0, d)

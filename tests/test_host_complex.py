@@ -119,3 +119,23 @@ def test_lattice_artefact_bounds_refused(sb):
     from shgo_b200 import functors as F
     with pytest.raises(LatticeArtefactError):
         sb.shgo(F.sphere, [(-3.3, 7.1)] * 3, n=None, iters=2)
+
+
+@pytest.mark.parametrize("kw", [dict(n=None, iters=3), dict(n=30, iters=3), dict(n=70, iters=2)])
+def test_local_bounds_through_the_driver_seam(sb, kw):
+    """SHGO.construct_lcb_simplicial served by DeviceComplex.local_bounds --
+    identical boxes, and no neighbour object is created for them."""
+    from shgo_b200 import api, functors as F
+    s = sb.SHGO(F.styblinski_tang, [(-5.0, 4.0)] * 3, sampling_method="simplicial", **kw)
+    s.iterate_complex()
+    s.iterate_complex()
+    s.minimizers()
+    m = api.driver_module()
+    reference_method = m.SHGO._shgo_b200_saved_lcb
+    assert len(s.minimizer_pool) > 0
+    boxes = [s.construct_lcb_simplicial(v) for v in s.minimizer_pool]
+    assert len(s.HC.V._unlisted) == 0
+    for v, got in zip(s.minimizer_pool, boxes):
+        assert got == reference_method(s, v)          # walks v.nn: materialises the star
+        assert all(lo <= x <= hi for (lo, hi), x in zip(got, v.x))
+    assert len(s.HC.V._unlisted) > 0

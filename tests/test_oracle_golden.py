@@ -118,3 +118,18 @@ def test_simplicial_pools(name):
         ref = {tuple(p) for p in g[f"pool_x_{it}"]}
         assert pool == ref, (name, it)
         started |= ref
+
+
+def local_bounds_names():
+    return [str(s) for s in load_golden("local_bounds")["names"]]
+
+
+@pytest.mark.parametrize("name", local_bounds_names())
+def test_local_bounds(name):
+    """f2: construct_lcb_simplicial of every vertex (recorded through the reference's method)."""
+    g = load_golden("local_bounds")
+    x, edges, bounds = g[name + "_x"], g[name + "_edges"], g[name + "_bounds"]
+    row_ptr, col = orc.csr_from_edges(edges, len(x))
+    lo, hi = orc.local_bounds_csr(row_ptr, col, x, np.arange(len(x)), bounds)
+    assert np.array_equal(lo, g[name + "_lo"])
+    assert np.array_equal(hi, g[name + "_hi"])
