@@ -213,6 +213,13 @@ SHGO_B200_API int shgo_b200_count_nfev(const int64_t *row_ptr, const uint8_t *fe
  */
 SHGO_B200_API int shgo_b200_lattice_eval(int functor, int gset, int d, int gen, const double *tab,
                            uint64_t v0, uint64_t nv, double *f, uint8_t *feasible, void *stream);
+/* multi-GPU form: every value is also stored at the same offset of npeers further vectors
+ * (f_peers: HOST array of device pointers, e.g. the peers' copies of f opened with
+ * shgo_b200_ipc_open, each already advanced to the position of vertex v0) -- evaluation and the
+ * exchange of f are one kernel.  npeers <= 15. */
+SHGO_B200_API int shgo_b200_lattice_eval_push(int functor, int gset, int d, int gen, const double *tab,
+                                uint64_t v0, uint64_t nv, double *f, uint8_t *feasible,
+                                double *const *f_peers, int npeers, void *stream);
 /* coordinates of vertices v0 .. v0+nv-1, SoA [d][ld] */
 SHGO_B200_API int shgo_b200_lattice_coords(int d, int gen, const double *tab, uint64_t v0, uint64_t nv,
                              double *x_soa, uint64_t ld, void *stream);

@@ -34,10 +34,19 @@ int sm_count()
 // Persistent evaluation kernel: grid = k * SMs CTAs of 256 threads striding over tiles of
 // 256*P points.  Output: 8 B per point (+1 B feasibility flag), coalesced.
 // ---------------------------------------------------------------------------------------------
-template <class F, template <int> class SrcT>
+// Multi-GPU: the same value is also stored at the same offset of up to kMaxReplicas further
+// vectors -- the peers' copies of f, mapped over NVLink (CUDA IPC).  The "all-gather" of f then
+// costs no pass of its own: the remote stores drain while the FP64 pipe works on the next tile.
+constexpr int kMaxReplicas = 15;
+struct Replicas {
+    double *p[kMaxReplicas];
+    int n;
+};
+
+template <class F, template <int> class SrcT, bool PUSH>
 __global__ void __launch_bounds__(kEvalThreads)
 eval_kernel(typename SrcT<F::P>::Params sp, int d, double *__restrict__ f,
-            uint8_t *__restrict__ feasible)
+            uint8_t *__restrict__ feasible, const Replicas rep)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int P = F::P;
@@ -60,6 +69,11 @@ eval_kernel(typename SrcT<F::P>::Params sp, int d, double *__restrict__ f,
                 if (!feas || v != v) v = pos_inf();
                 fp[i * kEvalThreads] = v;
                 if (gp) gp[i * kEvalThreads] = feas ? 1 : 0;
+                if (PUSH) {
+#pragma unroll
+                    for (int r = 0; r < kMaxReplicas; ++r)  // static indices: stays in the constant bank
+                        if (r < rep.n) rep.p[r][first + threadIdx.x + i * kEvalThreads] = v;
+                }
             }
         } else {
 #pragma unroll
@@ -71,19 +85,24 @@ eval_kernel(typename SrcT<F::P>::Params sp, int d, double *__restrict__ f,
                     if (!feas || v != v) v = pos_inf();
                     f[idx] = v;
                     if (feasible) feasible[idx] = feas ? 1 : 0;
+                    if (PUSH) {
+#pragma unroll
+                        for (int r = 0; r < kMaxReplicas; ++r)
+                            if (r < rep.n) rep.p[r][idx] = v;
+                    }
                 }
             }
         }
     }
 }
 
-template <class F, template <int> class SrcT>
+template <class F, template <int> class SrcT, bool PUSH>
 static int launch_eval(const typename SrcT<F::P>::Params &sp, int d, uint64_t npoints, size_t smem,
-                       double *f, uint8_t *feasible, cudaStream_t st)
+                       double *f, uint8_t *feasible, cudaStream_t st, const Replicas &rep)
 {
     if (!F::dim_ok(d))
         return fail(SHGO_B200_ERR_ARG, "functor does not support dimension %d", d);
-    auto kern = eval_kernel<F, SrcT>;
+    auto kern = eval_kernel<F, SrcT, PUSH>;
     if (smem > 48 * 1024)
         SHGO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
@@ -94,19 +113,19 @@ static int launch_eval(const typename SrcT<F::P>::Params &sp, int d, uint64_t np
     uint64_t grid = (uint64_t)sm_count() * occ;
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, kEvalThreads, smem, st>>>(sp, d, f, feasible);
+    kern<<<(unsigned)grid, kEvalThreads, smem, st>>>(sp, d, f, feasible, rep);
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;
 }
 
-template <template <int> class SrcT, class MakeParams, class SmemFn>
+template <template <int> class SrcT, bool PUSH = false, class MakeParams, class SmemFn>
 static int dispatch_eval(int functor, int gset, int d, uint64_t npoints, MakeParams mk, SmemFn smem,
-                         double *f, uint8_t *feasible, cudaStream_t st)
+                         double *f, uint8_t *feasible, cudaStream_t st, const Replicas &rep = Replicas{{}, 0})
 {
 #define SHGO_CASE(FID, GID, FT)                                                             \
     if (functor == (FID) && gset == (GID))                                                  \
-        return launch_eval<FT, SrcT>(mk.template operator()<FT::P>(), d, npoints,           \
-                                     smem.template operator()<FT::P>(), f, feasible, st);
+        return launch_eval<FT, SrcT, PUSH>(mk.template operator()<FT::P>(), d, npoints,           \
+                                     smem.template operator()<FT::P>(), f, feasible, st, rep);
     SHGO_CASE(SHGO_B200_F_ROSENBROCK, SHGO_B200_G_NONE, Rosenbrock)
     SHGO_CASE(SHGO_B200_F_RASTRIGIN, SHGO_B200_G_NONE, Rastrigin)
     SHGO_CASE(SHGO_B200_F_ACKLEY, SHGO_B200_G_NONE, Ackley)
@@ -376,6 +395,28 @@ int shgo_b200_lattice_eval(int functor, int gset, int d, int gen, const double *
                                      LatSmem{d, gen}, f, feasible, as_stream(stream));
 }
 
+
+int shgo_b200_lattice_eval_push(int functor, int gset, int d, int gen, const double *tab, uint64_t v0,
+                                uint64_t nv, double *f, uint8_t *feasible, double *const *f_peers,
+                                int npeers, void *stream)
+{
+    uint64_t ngrid, nvert;
+    if (int rc = lattice_counts(d, gen, &ngrid, &nvert)) return rc;
+    SHGO_REQUIRE(tab && f, "null pointer");
+    SHGO_REQUIRE(v0 + nv <= nvert, "vertex range exceeds the lattice (%llu vertices)",
+                 (unsigned long long)nvert);
+    SHGO_REQUIRE(npeers >= 0 && npeers <= kMaxReplicas, "at most %d peer copies (got %d)", kMaxReplicas,
+                 npeers);
+    SHGO_REQUIRE(npeers == 0 || f_peers, "null peer table");
+    if (nv == 0) return SHGO_B200_OK;
+    Replicas rep{{}, npeers};
+    for (int r = 0; r < npeers; ++r) {
+        SHGO_REQUIRE(f_peers[r], "null peer pointer %d", r);
+        rep.p[r] = f_peers[r];
+    }
+    return dispatch_eval<LatticeSrc, true>(functor, gset, d, nv, LatMk{tab, v0, nv, ngrid, d, gen},
+                                           LatSmem{d, gen}, f, feasible, as_stream(stream), rep);
+}
 
 int shgo_b200_lattice_coords(int d, int gen, const double *tab, uint64_t v0, uint64_t nv,
                              double *x_soa, uint64_t ld, void *stream)

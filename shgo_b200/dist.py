@@ -1,4 +1,4 @@
-"""Multi-GPU Sobol path: one process per GPU (torch.distributed), points sharded by index range.
+"""Multi-GPU hot path: one process per GPU (torch.distributed), vertices sharded by index range.
 
 SURVEY.md section 8(e): rank r of G owns Sobol indices / graph rows [r n/G, (r+1) n/G).  Point generation
 has a closed-form skip-ahead, so every shard generates and evaluates locally with no communication.
@@ -227,3 +227,120 @@ class ShardedSobolIteration:
                 p.close()
             self.peer = None
             self.peers = []
+
+
+def split_range(n, world, rank):
+    """[a, b) of `rank` when n items are dealt out as evenly as contiguous ranges allow"""
+    return rank * n // world, (rank + 1) * n // world
+
+
+class ShardedLatticeIteration:
+    """One whole generation of the simplicial hypercube complex over all ranks of `group`
+    (lattice path).
+
+    Every rank owns an equal share of the grid vertices AND of the cell centroids (their stars cost
+    very differently, so each kind is dealt out separately) and keeps a full-size copy of f: the
+    adjacency is implicit and a star reaches across the whole id range.  Exchanges:
+
+      'push'       (GPUs) the copies of f are cudaMalloc'ed, exported with CUDA IPC and mapped into
+                   every rank; the evaluation kernel stores each value into all copies at once over
+                   NVLink (shgo_b200_lattice_eval_push), so there is no separate all-gather pass.
+                   One stream-ordered barrier per generation; two alternating sets of copies make a
+                   second barrier unnecessary (see ShardedSobolIteration).
+      'allreduce'  plain collective baseline (NCCL on GPUs, gloo in the CPU tests): every rank
+                   evaluates its ranges into a zero-filled vector, one all_reduce(SUM) completes it
+                   (x + 0 is exact; infeasible vertices are +inf on exactly one rank).
+    """
+
+    def __init__(self, functor, gset, d, gen, tab, group=None, exchange="push"):
+        from . import lattice as lat
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.functor, self.gset, self.d, self.gen, self.tab = functor, gset, d, gen, tab
+        self.nv, self.ngrid = lat.counts(d, gen)
+        g0, g1 = split_range(self.ngrid, self.world, self.rank)
+        c0, c1 = split_range(self.nv - self.ngrid, self.world, self.rank)
+        # the two id ranges of this rank: (first vertex, count)
+        self.ranges = [(g0, g1 - g0), (self.ngrid + c0, c1 - c0)]
+        self.exchange = exchange if self.world > 1 else "none"
+        dev = tab.device
+        self.dev = dev
+        self.peers = []
+        if self.exchange == "push":
+            self.peers = [PeerMappedVector(self.nv, group), PeerMappedVector(self.nv, group)]
+            self._comm = torch.cuda.Stream(device=dev)
+            self._token = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.f = self.peers[0].local
+        else:
+            self.f = torch.zeros(self.nv, dtype=torch.float64, device=dev)
+        self._k = 0
+        self.feas = [torch.empty(max(n, 1), dtype=torch.uint8, device=dev)[:n] for _, n in self.ranges]
+        self.is_min = [torch.empty(max(n, 1), dtype=torch.uint8, device=dev)[:n] for _, n in self.ranges]
+        self.work = [hp.PoolWorkspace(max(n, 1), max(n, 1), dev) for _, n in self.ranges]
+        self._star_tmp = None
+
+    def step(self, events=None):
+        if self.exchange == "push":
+            pv = self.peers[self._k & 1]
+            self._k += 1
+            self.f = pv.local
+            others = [p for r, p in enumerate(pv.peer_ptrs) if r != self.rank]
+            for (v0, n), feas in zip(self.ranges, self.feas):
+                hp.lattice_eval_push(self.functor, self.gset, self.d, self.gen, self.tab, v0, n,
+                                     self.f[v0:v0 + n], feas, [p + 8 * v0 for p in others])
+            # "every copy of f is complete": stream-ordered, joined before the star test
+            main = torch.cuda.current_stream()
+            self._comm.wait_stream(main)
+            with torch.cuda.stream(self._comm):
+                dist.all_reduce(self._token, group=self.group)
+            main.wait_stream(self._comm)
+        else:
+            if self.exchange == "allreduce":
+                self.f.zero_()
+            for (v0, n), feas in zip(self.ranges, self.feas):
+                hp.lattice_eval(self.functor, self.gset, self.d, self.gen, self.tab, v0, n,
+                                f=self.f[v0:v0 + n], feasible=feas)
+            if self.exchange == "allreduce":
+                dist.all_reduce(self.f, group=self.group)
+        if events:
+            events[0].record()
+        for (v0, n), out in zip(self.ranges, self.is_min):
+            hp.lattice_star(self.d, self.gen, self.f, v0, n, is_min=out, tmp=self._tmp(n))
+        if events:
+            events[1].record()
+        for (v0, n), flags, w in zip(self.ranges, self.is_min, self.work):
+            hp.compact_pool(flags, base=v0, work=w)
+
+    def _tmp(self, n):
+        ws = _lib.lib().shgo_b200_lattice_star_workspace(n)
+        if self._star_tmp is None or self._star_tmp.numel() < ws:
+            self._star_tmp = torch.empty(ws, dtype=torch.uint8, device=self.dev)
+        return self._star_tmp
+
+    def local_pool(self):
+        parts = []
+        for w in self.work:
+            c = int(w.count[0].item())
+            parts.append(w.idx[:min(c, w.cap)])
+        return torch.cat(parts)
+
+    def global_pool(self):
+        """ascending pool (vertex ids) of the whole complex, on every rank"""
+        mine = self.local_pool().cpu().numpy()
+        if self.world > 1:
+            parts = [None] * self.world
+            dist.all_gather_object(parts, mine, group=self.group)
+            mine = np.concatenate(parts)
+        return np.sort(mine)
+
+    def global_nfev(self):
+        t = sum(f.sum(dtype=torch.int64) for f in self.feas).reshape(1).clone()
+        if self.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def close(self):
+        for p in self.peers:
+            p.close()
+        self.peers = []

@@ -285,6 +285,17 @@ def lattice_eval(functor, gset, d, gen, tab, v0, nv, f=None, feasible=None):
     return f, feasible
 
 
+def lattice_eval_push(functor, gset, d, gen, tab, v0, nv, f, feasible, peer_ptrs):
+    """lattice_eval whose values are also stored into the peers' copies of f (multi-GPU): f is the
+    rank's slice for vertices v0.., peer_ptrs the integer device addresses of the same position in
+    every peer's vector (CUDA-IPC mappings)."""
+    import ctypes
+    arr = (ctypes.c_void_p * max(len(peer_ptrs), 1))(*peer_ptrs)
+    _lib.call("shgo_b200_lattice_eval_push", functor, gset, d, gen, _ptr(tab), v0, nv, _ptr(f),
+              _ptr(feasible), arr, len(peer_ptrs), _stream())
+    return f, feasible
+
+
 def lattice_coords(d, gen, tab, v0, nv):
     x = torch.empty((d, nv), dtype=torch.float64, device=tab.device)
     _lib.call("shgo_b200_lattice_coords", d, gen, _ptr(tab), v0, nv, _ptr(x), max(nv, 1), _stream())

@@ -129,7 +129,14 @@ def _bounds_from_tab(tab):
 def lattice_eval(functor, gset, d, gen, tab, v0, nv, f=None, feasible=None):
     x = orc.lattice_coords(_bounds_from_tab(tab), gen)[v0:v0 + nv]
     fo, fe = orc.eval_points(_FN[functor], _GN[gset], x)
-    return torch.from_numpy(fo), torch.from_numpy(fe)
+    fo, fe = torch.from_numpy(fo), torch.from_numpy(fe)
+    if f is not None:
+        f.copy_(fo)
+        fo = f
+    if feasible is not None:
+        feasible.copy_(fe)
+        fe = feasible
+    return fo, fe
 
 
 def lattice_coords(d, gen, tab, v0, nv):
@@ -140,7 +147,11 @@ def lattice_coords(d, gen, tab, v0, nv):
 def lattice_star(d, gen, f, v0=0, nv=None, is_min=None, tmp=None):
     out = orc.lattice_star(d, gen, f.numpy())
     nv = len(out) - v0 if nv is None else nv
-    return torch.from_numpy(out[v0:v0 + nv].copy())
+    res = torch.from_numpy(out[v0:v0 + nv].copy())
+    if is_min is not None:
+        is_min.copy_(res)
+        return is_min
+    return res
 
 
 def local_bounds_csr(row_ptr, col, x_soa, pool, bounds):

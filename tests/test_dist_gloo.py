@@ -60,6 +60,56 @@ def test_sharded_iteration_matches_single_rank(world):
     assert int(z["nfev"]) == n
 
 
+def _lattice_worker(rank, world, init_file, out_dir, d, gen):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    from _pytest.monkeypatch import MonkeyPatch
+    import fake_hotpath
+    fake_hotpath.install(MonkeyPatch())
+    from shgo_b200 import dist as sd
+    from shgo_b200 import lattice
+    dist.init_process_group("gloo", init_method="file://" + init_file, rank=rank, world_size=world)
+    try:
+        bounds = [(-5.12, 5.12)] * d
+        tab = torch.from_numpy(lattice.coordinate_tables(bounds, gen))
+        it = sd.ShardedLatticeIteration(1, 0, d, gen, tab, exchange="allreduce")
+        it.step()
+        it.step()
+        pool, nfev = it.global_pool(), it.global_nfev()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "out.npz"), pool=pool, nfev=nfev,
+                     ranges=np.array(it.ranges))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,d,gen", [(2, 3, 2), (4, 2, 3), (2, 3, 0)])
+def test_sharded_lattice_generation_matches_single_rank(world, d, gen):
+    """SURVEY.md 8(e), lattice path: grid vertices and centroids dealt out separately; the union of
+    the ranks' pools equals the oracle's pool of the whole generation."""
+    from oracle import oracle as orc
+    with tempfile.TemporaryDirectory() as tmp:
+        init_file = os.path.join(tmp, "init")
+        mp.spawn(_lattice_worker, args=(world, init_file, tmp, d, gen), nprocs=world, join=True)
+        z = np.load(os.path.join(tmp, "out.npz"))
+    bounds = [(-5.12, 5.12)] * d
+    x = orc.lattice_coords(bounds, gen)
+    f, _ = orc.eval_points("rastrigin", None, x)
+    ref = orc.compact_pool(orc.lattice_star(d, gen, f))
+    assert np.array_equal(z["pool"], ref)
+    assert int(z["nfev"]) == len(x)
+
+
+def test_split_range_covers_everything():
+    from shgo_b200.dist import split_range
+    for n in (0, 1, 7, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            parts = [split_range(n, world, r) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+
+
 def test_shard_range():
     from shgo_b200.dist import shard_range
     assert [shard_range(1 << 10, 4, r) for r in range(4)] == [(0, 256), (256, 256), (512, 256), (768, 256)]
