@@ -122,6 +122,31 @@ def cpu_run(log2n, repeats):
     return n, times, len(pool), nfev, orc.num_threads()
 
 
+def python_driver_run(n=4096, d=3):
+    """The reference's own Python path (scipy's vendored copy of the driver + Complex; the GPU box
+    has no /root/reference) on a bounded sample: Sobol n points in d-D -> qhull -> vf_to_vv ->
+    process_pools -> minimizers, one core.  Returns points/s with and without the qhull time."""
+    import numpy as np
+    from scipy.optimize import _shgo as drv
+    from scipy.spatial import Delaunay
+
+    def st(x):
+        return 0.5 * np.sum(x ** 4 - 16 * x ** 2 + 5 * x)
+
+    s = drv.SHGO(st, [(-5.0, 5.0)] * d, n=n, iters=1, sampling_method="sobol")
+    t0 = time.perf_counter()
+    s.iterate_complex()
+    s.minimizers()
+    total = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Delaunay(s.C)
+    qhull = time.perf_counter() - t0
+    return {"value": n / total, "value_without_qhull": n / max(total - qhull, 1e-9), "unit": "points/s",
+            "cores": 1, "sample": "scipy.optimize._shgo (vendored copy of the reference's driver and "
+            "Python Complex): Styblinski-Tang %d-D, Sobol n=%d, iterate_complex + minimizers; "
+            "qhull %.2f s of %.2f s" % (d, n, qhull, total)}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -384,7 +409,7 @@ def main():
     }
     if e2e:
         out["e2e"] = e2e
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # reported at N = 1 only
         ncpu, times, npool, nfev_c, cores = cpu_run(args.cpu_log2n, 3)
         best = min(times)
         out["cpu_baseline"] = {
@@ -392,6 +417,10 @@ def main():
             "sample": "oracle C port (OpenMP, %d threads) of the same step on 2^%d points (degree "
                       "%d graph), best of 3; the Python reference itself runs ~1.5e4 points/s "
                       "single-core (BASELINE.md section 2)" % (cores, args.cpu_log2n, args.cpu_log2n)}
+        try:
+            out["cpu_baseline"]["python_reference"] = python_driver_run()
+        except Exception as e:          # informational only
+            out["cpu_baseline"]["python_reference"] = {"unavailable": repr(e)[:120]}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
