@@ -216,10 +216,17 @@ SHGO_B200_API int shgo_b200_lattice_eval(int functor, int gset, int d, int gen, 
 /* multi-GPU form: every value is also stored at the same offset of npeers further vectors
  * (f_peers: HOST array of device pointers, e.g. the peers' copies of f opened with
  * shgo_b200_ipc_open, each already advanced to the position of vertex v0) -- evaluation and the
- * exchange of f are one kernel.  npeers <= 15. */
+ * exchange of f are one kernel.  npeers <= 15.
+ * part / nparts / granule: the id range is cut into granules of `granule` consecutive vertices (a
+ * power of two >= SHGO_B200_LATTICE_MIN_GRANULE) and only the granules with (granule index %
+ * nparts) == part are evaluated (the others are left untouched) -- GPU `part` of `nparts`;
+ * granule-cyclic so that the very uneven star-test cost of a generation spreads over the GPUs.
+ * v0 must be a multiple of the granule if nparts > 1. */
+#define SHGO_B200_LATTICE_MIN_GRANULE 4096
 SHGO_B200_API int shgo_b200_lattice_eval_push(int functor, int gset, int d, int gen, const double *tab,
                                 uint64_t v0, uint64_t nv, double *f, uint8_t *feasible,
-                                double *const *f_peers, int npeers, void *stream);
+                                double *const *f_peers, int npeers, int part, int nparts, uint32_t granule,
+                                void *stream);
 /* coordinates of vertices v0 .. v0+nv-1, SoA [d][ld] */
 SHGO_B200_API int shgo_b200_lattice_coords(int d, int gen, const double *tab, uint64_t v0, uint64_t nv,
                              double *x_soa, uint64_t ld, void *stream);
@@ -229,6 +236,11 @@ SHGO_B200_API int shgo_b200_lattice_coords(int d, int gen, const double *tab, ui
 SHGO_B200_API size_t shgo_b200_lattice_star_workspace(uint64_t nv);
 SHGO_B200_API int shgo_b200_lattice_star(int d, int gen, const double *f, uint64_t v0, uint64_t nv,
                            uint8_t *is_min, void *tmp, size_t tmp_bytes, void *stream);
+/* the same for the granules owned by `part` of `nparts` (see shgo_b200_lattice_eval_push); is_min
+ * still has nv entries, those of other parts' vertices are set to 0 */
+SHGO_B200_API int shgo_b200_lattice_star_part(int d, int gen, const double *f, uint64_t v0, uint64_t nv,
+                                int part, int nparts, uint32_t granule, uint8_t *is_min, void *tmp,
+                                size_t tmp_bytes, void *stream);
 
 /* ---- local bounds of pool vertices -------------------------------------
  * Replaces SHGO.construct_lcb_simplicial, shgo/_shgo.py:1246-1270: per pool vertex and axis, the

@@ -38,10 +38,11 @@ SIGNATURES = {
     "shgo_b200_argmin": (_i, [_vp, _vp, _u64, _vp, _vp, _vp, _sz, _vp]),
     "shgo_b200_count_nfev": (_i, [_vp, _vp, _u64, _vp, _vp]),
     "shgo_b200_lattice_eval": (_i, [_i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp]),
-    "shgo_b200_lattice_eval_push": (_i, [_i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp, _i, _vp]),
+    "shgo_b200_lattice_eval_push": (_i, [_i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp, _i, _i, _i, ctypes.c_uint32, _vp]),
     "shgo_b200_lattice_coords": (_i, [_i, _i, _vp, _u64, _u64, _vp, _u64, _vp]),
     "shgo_b200_lattice_star_workspace": (_sz, [_u64]),
     "shgo_b200_lattice_star": (_i, [_i, _i, _vp, _u64, _u64, _vp, _vp, _sz, _vp]),
+    "shgo_b200_lattice_star_part": (_i, [_i, _i, _vp, _u64, _u64, _i, _i, ctypes.c_uint32, _vp, _vp, _sz, _vp]),
     "shgo_b200_local_bounds_csr": (_i, [_vp, _vp, _vp, _u64, _i, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "shgo_b200_lattice_local_bounds": (_i, [_i, _i, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "shgo_b200_ctx_create": (_i, [_i, _vp]),

@@ -41,6 +41,11 @@ constexpr int kMaxReplicas = 15;
 struct Replicas {
     double *p[kMaxReplicas];
     int n;
+    // ownership: of the granules of SHGO_B200_LATTICE_GRANULE consecutive ids (counted from id0)
+    // this launch evaluates those with granule % nparts == part
+    uint32_t part, nparts;
+    uint64_t id0;
+    int granule_log2;
 };
 
 template <class F, template <int> class SrcT, bool PUSH>
@@ -53,6 +58,9 @@ eval_kernel(typename SrcT<F::P>::Params sp, int d, double *__restrict__ f,
     SrcT<P> src(sp, smem);
     const uint64_t ntiles = src.num_tiles();
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (PUSH && rep.nparts > 1 &&
+            ((rep.id0 + tile * (uint64_t)SrcT<P>::kTile) >> rep.granule_log2) % rep.nparts != rep.part)
+            continue;
         src.begin_tile(tile);
         double fv[P];
         uint32_t ok;
@@ -120,7 +128,7 @@ static int launch_eval(const typename SrcT<F::P>::Params &sp, int d, uint64_t np
 
 template <template <int> class SrcT, bool PUSH = false, class MakeParams, class SmemFn>
 static int dispatch_eval(int functor, int gset, int d, uint64_t npoints, MakeParams mk, SmemFn smem,
-                         double *f, uint8_t *feasible, cudaStream_t st, const Replicas &rep = Replicas{{}, 0})
+                         double *f, uint8_t *feasible, cudaStream_t st, const Replicas &rep = Replicas{{}, 0, 0, 1, 0, 12})
 {
 #define SHGO_CASE(FID, GID, FT)                                                             \
     if (functor == (FID) && gset == (GID))                                                  \
@@ -398,7 +406,7 @@ int shgo_b200_lattice_eval(int functor, int gset, int d, int gen, const double *
 
 int shgo_b200_lattice_eval_push(int functor, int gset, int d, int gen, const double *tab, uint64_t v0,
                                 uint64_t nv, double *f, uint8_t *feasible, double *const *f_peers,
-                                int npeers, void *stream)
+                                int npeers, int part, int nparts, uint32_t granule, void *stream)
 {
     uint64_t ngrid, nvert;
     if (int rc = lattice_counts(d, gen, &ngrid, &nvert)) return rc;
@@ -408,8 +416,15 @@ int shgo_b200_lattice_eval_push(int functor, int gset, int d, int gen, const dou
     SHGO_REQUIRE(npeers >= 0 && npeers <= kMaxReplicas, "at most %d peer copies (got %d)", kMaxReplicas,
                  npeers);
     SHGO_REQUIRE(npeers == 0 || f_peers, "null peer table");
+    SHGO_REQUIRE(nparts >= 1 && part >= 0 && part < nparts, "bad part %d of %d", part, nparts);
+    SHGO_REQUIRE(granule >= SHGO_B200_LATTICE_MIN_GRANULE && (granule & (granule - 1)) == 0,
+                 "granule must be a power of two >= %d (got %u)", SHGO_B200_LATTICE_MIN_GRANULE, granule);
+    SHGO_REQUIRE(nparts == 1 || v0 % granule == 0,
+                 "v0 must be a multiple of the granule when the range is dealt out in parts");
     if (nv == 0) return SHGO_B200_OK;
-    Replicas rep{{}, npeers};
+    int glog = 0;
+    while ((1u << glog) < granule) ++glog;
+    Replicas rep{{}, npeers, (uint32_t)part, (uint32_t)nparts, v0, glog};
     for (int r = 0; r < npeers; ++r) {
         SHGO_REQUIRE(f_peers[r], "null peer pointer %d", r);
         rep.p[r] = f_peers[r];

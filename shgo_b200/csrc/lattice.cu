@@ -146,7 +146,7 @@ struct StarWalk {
 template <int D>
 __global__ void __launch_bounds__(256)
 lattice_star_kernel(int gen, const double *__restrict__ f, uint64_t v0, uint64_t nv, uint64_t ngrid64,
-                    uint8_t *__restrict__ flags)
+                    uint8_t *__restrict__ flags, uint32_t part, uint32_t nparts, int granule_log2)
 {
     const LatticeGeom<D> g(gen, (uint32_t)ngrid64);
     const int lane = threadIdx.x & 31;
@@ -155,6 +155,8 @@ lattice_star_kernel(int gen, const double *__restrict__ f, uint64_t v0, uint64_t
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int kQuick = 2 * D < (1 << D) ? 2 * D : (1 << D);
     for (uint64_t base = gwarp << 5; base < nv; base += nwarps << 5) {
+        // multi-GPU: only the granules dealt to this part (the others' flags were zeroed)
+        if (nparts > 1 && ((v0 + base) >> granule_log2) % nparts != part) continue;
         const uint64_t lv = base + lane;
         const bool valid = lv < nv;
         const uint32_t v = (uint32_t)(v0 + (valid ? lv : 0));
@@ -327,13 +329,15 @@ static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 template <int D>
 static int launch_lattice_star(int gen, const double *f, uint64_t v0, uint64_t nv, uint64_t ngrid,
-                               uint8_t *flags, void *tmp, cudaStream_t st)
+                               uint8_t *flags, void *tmp, cudaStream_t st, int part, int nparts, int granule_log2)
 {
+    if (nparts > 1) SHGO_CUDA_TRY(cudaMemsetAsync(flags, 0, nv, st));
     uint64_t blocks = (nv + 255) / 256;  // 8 warps per CTA, 32 vertices per warp per pass
     uint64_t cap = (uint64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    lattice_star_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(gen, f, v0, nv, ngrid, flags);
+    lattice_star_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(gen, f, v0, nv, ngrid, flags, (uint32_t)part,
+                                                             (uint32_t)nparts, granule_log2);
     // stage C on the undecided vertices
     unsigned char *p = static_cast<unsigned char *>(tmp);
     int64_t *cand = reinterpret_cast<int64_t *>(p);
@@ -359,6 +363,19 @@ extern "C" size_t shgo_b200_lattice_star_workspace(uint64_t nv)
 extern "C" int shgo_b200_lattice_star(int d, int gen, const double *f, uint64_t v0, uint64_t nv,
                                       uint8_t *is_min, void *tmp, size_t tmp_bytes, void *stream)
 {
+    return shgo_b200_lattice_star_part(d, gen, f, v0, nv, 0, 1, SHGO_B200_LATTICE_MIN_GRANULE, is_min, tmp, tmp_bytes,
+                                       stream);
+}
+
+extern "C" int shgo_b200_lattice_star_part(int d, int gen, const double *f, uint64_t v0, uint64_t nv,
+                                           int part, int nparts, uint32_t granule, uint8_t *is_min,
+                                           void *tmp, size_t tmp_bytes, void *stream)
+{
+    SHGO_REQUIRE(nparts >= 1 && part >= 0 && part < nparts, "bad part %d of %d", part, nparts);
+    SHGO_REQUIRE(granule >= 32 && (granule & (granule - 1)) == 0, "granule must be a power of two >= 32");
+    int glog = 0;
+    while ((1u << glog) < granule) ++glog;
+    SHGO_REQUIRE(nparts == 1 || v0 % 32 == 0, "v0 must be a multiple of 32 when the range is dealt out in parts");
     SHGO_REQUIRE(d >= 1 && d <= 12, "lattice star test supports 1 <= d <= 12 (got %d)", d);
     SHGO_REQUIRE(gen >= 0 && gen <= 20, "generation %d outside 0..20", gen);
     double ng = 1, nc = 1;
@@ -379,7 +396,7 @@ extern "C" int shgo_b200_lattice_star(int d, int gen, const double *f, uint64_t 
     cudaStream_t st = as_stream(stream);
     switch (d) {
 #define SHGO_D(DD) \
-    case DD: return launch_lattice_star<DD>(gen, f, v0, nv, ngrid, is_min, tmp, st);
+    case DD: return launch_lattice_star<DD>(gen, f, v0, nv, ngrid, is_min, tmp, st, part, nparts, glog);
         SHGO_D(1) SHGO_D(2) SHGO_D(3) SHGO_D(4) SHGO_D(5) SHGO_D(6)
         SHGO_D(7) SHGO_D(8) SHGO_D(9) SHGO_D(10) SHGO_D(11) SHGO_D(12)
 #undef SHGO_D

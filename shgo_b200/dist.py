@@ -238,9 +238,12 @@ class ShardedLatticeIteration:
     """One whole generation of the simplicial hypercube complex over all ranks of `group`
     (lattice path).
 
-    Every rank owns an equal share of the grid vertices AND of the cell centroids (their stars cost
-    very differently, so each kind is dealt out separately) and keeps a full-size copy of f: the
-    adjacency is implicit and a star reaches across the whole id range.  Exchanges:
+    The adjacency is implicit and a star reaches across the whole id range, so every rank keeps a
+    full-size copy of f.  Ownership is granule-cyclic: the id range is cut into granules of
+    hp.LATTICE_GRANULE consecutive vertices and rank r evaluates / classifies granules r, r+G, ...
+    -- the cost of a star test is wildly uneven (a rejected vertex: a handful of reads; a true
+    minimiser of the 10-D complex: 59 048) and clusters in id space, contiguous slabs measured
+    0.21 .. 0.88 ms per rank at G = 8.  Exchanges:
 
       'push'       (GPUs) the copies of f are cudaMalloc'ed, exported with CUDA IPC and mapped into
                    every rank; the evaluation kernel stores each value into all copies at once over
@@ -248,21 +251,18 @@ class ShardedLatticeIteration:
                    One stream-ordered barrier per generation; two alternating sets of copies make a
                    second barrier unnecessary (see ShardedSobolIteration).
       'allreduce'  plain collective baseline (NCCL on GPUs, gloo in the CPU tests): every rank
-                   evaluates its ranges into a zero-filled vector, one all_reduce(SUM) completes it
-                   (x + 0 is exact; infeasible vertices are +inf on exactly one rank).
+                   evaluates its granules into a zero-filled vector, one all_reduce(SUM) completes
+                   it (x + 0 is exact; infeasible vertices are +inf on exactly one rank).
     """
 
-    def __init__(self, functor, gset, d, gen, tab, group=None, exchange="push"):
+    def __init__(self, functor, gset, d, gen, tab, group=None, exchange="push", granule=None):
         from . import lattice as lat
+        self.granule = hp.LATTICE_GRANULE if granule is None else int(granule)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.functor, self.gset, self.d, self.gen, self.tab = functor, gset, d, gen, tab
         self.nv, self.ngrid = lat.counts(d, gen)
-        g0, g1 = split_range(self.ngrid, self.world, self.rank)
-        c0, c1 = split_range(self.nv - self.ngrid, self.world, self.rank)
-        # the two id ranges of this rank: (first vertex, count)
-        self.ranges = [(g0, g1 - g0), (self.ngrid + c0, c1 - c0)]
         self.exchange = exchange if self.world > 1 else "none"
         dev = tab.device
         self.dev = dev
@@ -275,20 +275,26 @@ class ShardedLatticeIteration:
         else:
             self.f = torch.zeros(self.nv, dtype=torch.float64, device=dev)
         self._k = 0
-        self.feas = [torch.empty(max(n, 1), dtype=torch.uint8, device=dev)[:n] for _, n in self.ranges]
-        self.is_min = [torch.empty(max(n, 1), dtype=torch.uint8, device=dev)[:n] for _, n in self.ranges]
-        self.work = [hp.PoolWorkspace(max(n, 1), max(n, 1), dev) for _, n in self.ranges]
-        self._star_tmp = None
+        self.feas = torch.zeros(self.nv, dtype=torch.uint8, device=dev)   # stays 0 outside own granules
+        self.is_min = torch.empty(self.nv, dtype=torch.uint8, device=dev)
+        self.work = hp.PoolWorkspace(self.nv, self.nv, dev)
+        ws = _lib.lib().shgo_b200_lattice_star_workspace(self.nv)
+        self._star_tmp = torch.empty(ws, dtype=torch.uint8, device=dev)
+
+    def owned(self):
+        """boolean mask (host) of the vertices this rank owns"""
+        g = np.arange(self.nv) // self.granule
+        return (g % self.world) == self.rank
 
     def step(self, events=None):
+        d, gen, nv = self.d, self.gen, self.nv
         if self.exchange == "push":
             pv = self.peers[self._k & 1]
             self._k += 1
             self.f = pv.local
             others = [p for r, p in enumerate(pv.peer_ptrs) if r != self.rank]
-            for (v0, n), feas in zip(self.ranges, self.feas):
-                hp.lattice_eval_push(self.functor, self.gset, self.d, self.gen, self.tab, v0, n,
-                                     self.f[v0:v0 + n], feas, [p + 8 * v0 for p in others])
+            hp.lattice_eval_push(self.functor, self.gset, d, gen, self.tab, 0, nv, self.f, self.feas,
+                                 others, self.rank, self.world, self.granule)
             # "every copy of f is complete": stream-ordered, joined before the star test
             main = torch.cuda.current_stream()
             self._comm.wait_stream(main)
@@ -298,32 +304,21 @@ class ShardedLatticeIteration:
         else:
             if self.exchange == "allreduce":
                 self.f.zero_()
-            for (v0, n), feas in zip(self.ranges, self.feas):
-                hp.lattice_eval(self.functor, self.gset, self.d, self.gen, self.tab, v0, n,
-                                f=self.f[v0:v0 + n], feasible=feas)
+            hp.lattice_eval_push(self.functor, self.gset, d, gen, self.tab, 0, nv, self.f, self.feas, [],
+                                 self.rank, self.world, self.granule)
             if self.exchange == "allreduce":
                 dist.all_reduce(self.f, group=self.group)
         if events:
             events[0].record()
-        for (v0, n), out in zip(self.ranges, self.is_min):
-            hp.lattice_star(self.d, self.gen, self.f, v0, n, is_min=out, tmp=self._tmp(n))
+        hp.lattice_star(d, gen, self.f, 0, nv, is_min=self.is_min, tmp=self._star_tmp, part=self.rank,
+                        nparts=self.world, granule=self.granule)
         if events:
             events[1].record()
-        for (v0, n), flags, w in zip(self.ranges, self.is_min, self.work):
-            hp.compact_pool(flags, base=v0, work=w)
-
-    def _tmp(self, n):
-        ws = _lib.lib().shgo_b200_lattice_star_workspace(n)
-        if self._star_tmp is None or self._star_tmp.numel() < ws:
-            self._star_tmp = torch.empty(ws, dtype=torch.uint8, device=self.dev)
-        return self._star_tmp
+        hp.compact_pool(self.is_min, base=0, work=self.work)
 
     def local_pool(self):
-        parts = []
-        for w in self.work:
-            c = int(w.count[0].item())
-            parts.append(w.idx[:min(c, w.cap)])
-        return torch.cat(parts)
+        c = int(self.work.count[0].item())
+        return self.work.idx[:min(c, self.work.cap)]
 
     def global_pool(self):
         """ascending pool (vertex ids) of the whole complex, on every rank"""
@@ -335,7 +330,7 @@ class ShardedLatticeIteration:
         return np.sort(mine)
 
     def global_nfev(self):
-        t = sum(f.sum(dtype=torch.int64) for f in self.feas).reshape(1).clone()
+        t = self.feas.sum(dtype=torch.int64).reshape(1).clone()
         if self.world > 1:
             dist.all_reduce(t, group=self.group)
         return int(t.item())

@@ -285,14 +285,19 @@ def lattice_eval(functor, gset, d, gen, tab, v0, nv, f=None, feasible=None):
     return f, feasible
 
 
-def lattice_eval_push(functor, gset, d, gen, tab, v0, nv, f, feasible, peer_ptrs):
-    """lattice_eval whose values are also stored into the peers' copies of f (multi-GPU): f is the
-    rank's slice for vertices v0.., peer_ptrs the integer device addresses of the same position in
-    every peer's vector (CUDA-IPC mappings)."""
+LATTICE_GRANULE = 1 << 16   # default ownership granule of the multi-GPU lattice path (vertices)
+
+
+def lattice_eval_push(functor, gset, d, gen, tab, v0, nv, f, feasible, peer_ptrs, part=0, nparts=1,
+                      granule=LATTICE_GRANULE):
+    """lattice_eval of the granules owned by `part` of `nparts` (granule-cyclic), whose values are
+    also stored into the peers' copies of f (multi-GPU): f is the rank's slice for vertices v0..,
+    peer_ptrs the integer device addresses of the same position in every peer's vector (CUDA-IPC
+    mappings).  Entries of granules owned by other parts are left untouched."""
     import ctypes
     arr = (ctypes.c_void_p * max(len(peer_ptrs), 1))(*peer_ptrs)
     _lib.call("shgo_b200_lattice_eval_push", functor, gset, d, gen, _ptr(tab), v0, nv, _ptr(f),
-              _ptr(feasible), arr, len(peer_ptrs), _stream())
+              _ptr(feasible), arr, len(peer_ptrs), part, nparts, granule, _stream())
     return f, feasible
 
 
@@ -302,15 +307,16 @@ def lattice_coords(d, gen, tab, v0, nv):
     return x
 
 
-def lattice_star(d, gen, f, v0=0, nv=None, is_min=None, tmp=None):
+def lattice_star(d, gen, f, v0=0, nv=None, is_min=None, tmp=None, part=0, nparts=1, granule=LATTICE_GRANULE):
+    """part / nparts: classify only the granules owned by `part` (the other flags come back 0)"""
     nv = f.numel() - v0 if nv is None else nv
     if is_min is None:
         is_min = torch.empty(nv, dtype=torch.uint8, device=f.device)
     ws = _lib.lib().shgo_b200_lattice_star_workspace(nv)
     if tmp is None or tmp.numel() < ws:
         tmp = torch.empty(ws, dtype=torch.uint8, device=f.device)
-    _lib.call("shgo_b200_lattice_star", d, gen, _ptr(f), v0, nv, _ptr(is_min), _ptr(tmp), tmp.numel(),
-              _stream())
+    _lib.call("shgo_b200_lattice_star_part", d, gen, _ptr(f), v0, nv, part, nparts, granule, _ptr(is_min), _ptr(tmp),
+              tmp.numel(), _stream())
     return is_min
 
 

@@ -139,15 +139,33 @@ def lattice_eval(functor, gset, d, gen, tab, v0, nv, f=None, feasible=None):
     return fo, fe
 
 
+LATTICE_GRANULE = 1 << 16
+
+
+def _owned(v0, nv, part, nparts, granule):
+    return ((np.arange(v0, v0 + nv) // granule) % nparts) == part
+
+
+def lattice_eval_push(functor, gset, d, gen, tab, v0, nv, f, feasible, peer_ptrs, part=0, nparts=1,
+                      granule=LATTICE_GRANULE):
+    assert not peer_ptrs, "no peer memory on the CPU stand-in"
+    fo, fe = lattice_eval(functor, gset, d, gen, tab, v0, nv)
+    own = torch.from_numpy(_owned(v0, nv, part, nparts, granule))
+    f[own] = fo[own]
+    feasible[own] = fe[own]
+    return f, feasible
+
+
 def lattice_coords(d, gen, tab, v0, nv):
     x = orc.lattice_coords(_bounds_from_tab(tab), gen)[v0:v0 + nv]
     return torch.from_numpy(np.ascontiguousarray(x.T))
 
 
-def lattice_star(d, gen, f, v0=0, nv=None, is_min=None, tmp=None):
+def lattice_star(d, gen, f, v0=0, nv=None, is_min=None, tmp=None, part=0, nparts=1, granule=LATTICE_GRANULE):
     out = orc.lattice_star(d, gen, f.numpy())
     nv = len(out) - v0 if nv is None else nv
     res = torch.from_numpy(out[v0:v0 + nv].copy())
+    res[torch.from_numpy(~_owned(v0, nv, part, nparts, granule))] = 0
     if is_min is not None:
         is_min.copy_(res)
         return is_min
@@ -173,7 +191,7 @@ def install(monkeypatch):
     from shgo_b200 import hotpath as hp
     for name in ("SobolTables", "sobol_points", "eval_sobol", "eval_points", "mask_infeasible",
                  "csr_from_simplices", "first_seen", "star_csr", "star_csr_shard", "PoolWorkspace", "compact_pool", "argmin", "lattice_eval",
-                 "lattice_coords", "lattice_star", "local_bounds_csr", "lattice_local_bounds"):
+                 "lattice_coords", "lattice_star", "local_bounds_csr", "lattice_local_bounds", "lattice_eval_push"):
         monkeypatch.setattr(hp, name, globals()[name])
     monkeypatch.setattr(hp, "_require_cuda", lambda: None)
     monkeypatch.setattr(hp, "_dev", lambda device=None: CPU)

@@ -72,21 +72,21 @@ def _lattice_worker(rank, world, init_file, out_dir, d, gen):
     try:
         bounds = [(-5.12, 5.12)] * d
         tab = torch.from_numpy(lattice.coordinate_tables(bounds, gen))
-        it = sd.ShardedLatticeIteration(1, 0, d, gen, tab, exchange="allreduce")
+        it = sd.ShardedLatticeIteration(1, 0, d, gen, tab, exchange="allreduce", granule=4096)
         it.step()
         it.step()
         pool, nfev = it.global_pool(), it.global_nfev()
         if rank == 0:
-            np.savez(os.path.join(out_dir, "out.npz"), pool=pool, nfev=nfev,
-                     ranges=np.array(it.ranges))
+            np.savez(os.path.join(out_dir, "out.npz"), pool=pool, nfev=nfev, owned=int(it.owned().sum()))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,d,gen", [(2, 3, 2), (4, 2, 3), (2, 3, 0)])
+@pytest.mark.parametrize("world,d,gen", [(2, 5, 2), (4, 2, 6), (2, 3, 0)])
 def test_sharded_lattice_generation_matches_single_rank(world, d, gen):
-    """SURVEY.md 8(e), lattice path: grid vertices and centroids dealt out separately; the union of
-    the ranks' pools equals the oracle's pool of the whole generation."""
+    """SURVEY.md 8(e), lattice path: granule-cyclic ownership (4096 ids per granule: the cases
+    span 2, 3 and 1 granules); the union of the ranks' pools equals the oracle's pool of the whole
+    generation."""
     from oracle import oracle as orc
     with tempfile.TemporaryDirectory() as tmp:
         init_file = os.path.join(tmp, "init")

@@ -570,3 +570,35 @@ def test_lattice_local_bounds_vs_explicit_walk_10d(hp):
     assert np.array_equal(lo.cpu().numpy(), want_lo) and np.array_equal(hi.cpu().numpy(), want_hi)
     assert hp.lattice_local_bounds(d, gen, torch.from_numpy(tab_h).cuda(),
                                    torch.zeros(0, dtype=torch.int64).cuda(), bounds)[0].shape == (0, d)
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 8])
+def test_lattice_granule_cyclic_parts_emulated_on_one_gpu(hp, nparts):
+    """Multi-GPU lattice path with every 'GPU' living on this one: each part evaluates its granules
+    and pushes them into all copies of f (peer pointers = other local vectors); the union of the
+    parts' flags must equal the single-launch result.  (Real multi-process path:
+    tools/check_sharded_lattice.py under torchrun.)"""
+    from shgo_b200 import lattice
+    d, gen = 6, 2                      # 15 625 + 4 096 = 19 721 vertices: 5 granules, last one partial
+    bounds = [(-32.768, 32.768)] * d
+    tab = torch.from_numpy(lattice.coordinate_tables(bounds, gen)).cuda()
+    nv, _ = orc.lattice_nvert(d, gen)
+    fid, gid = _ids("ackley", None)
+    f_ref, feas_ref = hp.lattice_eval(fid, gid, d, gen, tab, 0, nv)
+    ref = hp.lattice_star(d, gen, f_ref)
+    copies = [torch.full((nv,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(nparts)]
+    feas = [torch.zeros(nv, dtype=torch.uint8, device="cuda") for _ in range(nparts)]
+    for p in range(nparts):
+        others = [c.data_ptr() for q, c in enumerate(copies) if q != p]
+        hp.lattice_eval_push(fid, gid, d, gen, tab, 0, nv, copies[p], feas[p], others, p, nparts, 4096)
+    for c in copies:                   # every copy is complete and bit-identical
+        assert torch.equal(c, f_ref)
+    assert torch.equal(sum(feas), feas_ref)
+    union = torch.zeros(nv, dtype=torch.uint8, device="cuda")
+    owner = (torch.arange(nv, device="cuda") // 4096) % nparts
+    for p in range(nparts):
+        fl = hp.lattice_star(d, gen, copies[p], part=p, nparts=nparts, granule=4096)
+        assert int(fl[owner != p].sum().item()) == 0
+        union += fl
+    assert torch.equal(union, ref)
+    assert np.array_equal(ref.cpu().numpy(), orc.lattice_star(d, gen, f_ref.cpu().numpy()))
