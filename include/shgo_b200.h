@@ -164,11 +164,14 @@ SHGO_B200_API int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t 
  * (own0 = my_shard * rows_per_shard), so that a caller can pipeline chunks: phase 2 of one chunk
  * (NVLink bound) overlaps phase 1 of the next (HBM bound) on another stream.  flags / feasible are
  * indexed relative to row0, f_own relative to own0.
- * row_ptr / col are this shard's slices addressed with GLOBAL row ids / offsets (virtual bases). */
+ * row_ptr / col are this shard's slices addressed with GLOBAL row ids / offsets (virtual bases).
+ * remote_at_ends != 0 (same promise as for phase 2, see above): every row is trimmed to its local
+ * middle part once and then walked like a single-GPU row, without a per-neighbour ownership test. */
 SHGO_B200_API int shgo_b200_star_csr_local(const int64_t *row_ptr, const int32_t *col, const double *f_own,
                              const uint8_t *feasible, uint64_t own0, uint64_t own_rows,
-                             uint64_t row0, uint64_t rows, uint64_t nnz_hint, uint8_t *flags,
-                             void *cand_ws, size_t cand_ws_bytes, uint64_t *nfev, void *stream);
+                             uint64_t row0, uint64_t rows, uint64_t nnz_hint, int remote_at_ends,
+                             uint8_t *flags, void *cand_ws, size_t cand_ws_bytes, uint64_t *nfev,
+                             void *stream);
 SHGO_B200_API size_t shgo_b200_star_local_workspace(uint64_t rows);
 SHGO_B200_API size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap);
 SHGO_B200_API int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col,

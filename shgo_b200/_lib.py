@@ -25,7 +25,8 @@ SIGNATURES = {
     "shgo_b200_first_seen": (_i, [_vp, _u64, _i, _u64, _vp, _vp]),
     "shgo_b200_star_csr": (_i, [_vp, _vp, _vp, _u64, _u64, _u64, _vp, _vp]),
     "shgo_b200_star_csr_nfev": (_i, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp]),
-    "shgo_b200_star_csr_local": (_i, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _vp, _sz, _vp, _vp]),
+    "shgo_b200_star_csr_local": (_i, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _u64, _u64, _i, _vp, _vp, _sz, _vp,
+                                      _vp]),
     "shgo_b200_star_local_workspace": (_sz, [_u64]),
     "shgo_b200_star_remote_workspace": (_sz, [_u64, _u64]),
     "shgo_b200_star_csr_remote": (_i, [_vp, _vp, _vp, _vp, _i, _u64, _i, _u64, _u64, _i, _vp, _vp, _u64, _vp, _sz, _vp]),

@@ -179,7 +179,7 @@ class ShardedSobolIteration:
                 r0 = self.row0 + c * per
                 nr = per if c < C - 1 else self.rows - c * per
                 hp.star_csr_local(self.row_ptr, self.col, self.row0, self.f_my, self.feas, self.is_min,
-                                  self._nfev_parts[c:c + 1], self.off0, r0, nr, self._cand_ws)
+                                  self._nfev_parts[c:c + 1], self.off0, r0, nr, self._cand_ws, self.remote_at_ends)
                 self._remote.wait_stream(main)
                 with torch.cuda.stream(self._remote):
                     hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table,

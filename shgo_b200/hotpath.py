@@ -182,9 +182,10 @@ def star_csr_shard(row_ptr_local, col_local, row0, f_all, feasible, is_min, nfev
 
 
 def star_csr_local(row_ptr_local, col_local, own0, f_own, feasible, flags, nfev, off0=None, r0=None,
-                   nrows=None, cand_ws=None):
+                   nrows=None, cand_ws=None, remote_at_ends=False):
     """Multi-GPU phase 1: rows [r0, r0+nrows) of this GPU's shard (default: all of it) against its
-    OWN shard of f; flags 0 / 1 / 2 (candidate).  feasible / flags are whole-shard tensors."""
+    OWN shard of f; flags 0 / 1 / 2 (candidate).  feasible / flags are whole-shard tensors.
+    remote_at_ends: promise that other GPUs' vertices sit at the two ends of every row (faster walk)."""
     own_rows = row_ptr_local.numel() - 1
     if off0 is None:
         off0 = int(row_ptr_local[0].item())
@@ -195,7 +196,7 @@ def star_csr_local(row_ptr_local, col_local, own0, f_own, feasible, flags, nfev,
     _lib.call("shgo_b200_star_csr_local", row_ptr_local.data_ptr() - own0 * 8,
               col_local.data_ptr() - off0 * 4, _ptr(f_own),
               feasible.data_ptr() + sh if feasible is not None else None, own0, own_rows, r0, nrows, hint,
-              flags.data_ptr() + sh, _ptr(cand_ws), cand_ws.numel() if cand_ws is not None else 0, _ptr(nfev),
+              1 if remote_at_ends else 0, flags.data_ptr() + sh, _ptr(cand_ws), cand_ws.numel() if cand_ws is not None else 0, _ptr(nfev),
               _stream())
     return flags
 
@@ -285,7 +286,7 @@ def lattice_eval(functor, gset, d, gen, tab, v0, nv, f=None, feasible=None):
     return f, feasible
 
 
-LATTICE_GRANULE = 1 << 16   # default ownership granule of the multi-GPU lattice path (vertices)
+LATTICE_GRANULE = 4096   # default ownership granule of the multi-GPU lattice path (vertices; measured best at N = 8)
 
 
 def lattice_eval_push(functor, gset, d, gen, tab, v0, nv, f, feasible, peer_ptrs, part=0, nparts=1,

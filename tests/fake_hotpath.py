@@ -139,7 +139,7 @@ def lattice_eval(functor, gset, d, gen, tab, v0, nv, f=None, feasible=None):
     return fo, fe
 
 
-LATTICE_GRANULE = 1 << 16
+LATTICE_GRANULE = 4096
 
 
 def _owned(v0, nv, part, nparts, granule):

@@ -452,6 +452,17 @@ def test_two_phase_sharded_star_emulated_on_one_gpu(hp, nshards):
             hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, fl3, None,
                                remote_at_ends=True, cand_ws=cws)
             assert torch.equal(fl3, flags)
+            # phase 1 trimming every row to its local middle part (the same promise)
+            fl4 = torch.empty_like(flags)
+            nf4 = torch.zeros(1, dtype=torch.int64, device="cuda")
+            hp.star_csr_local(rp_l, col_l, row0, f_sh[s], None, fl4, nf4, cand_ws=cws, remote_at_ends=True)
+            f4 = fl4.cpu().numpy()
+            # identical, except that a row WITHOUT local neighbours is always left to phase 2 (the
+            # checked walk already rejects it when its own f is +inf)
+            assert np.all((f4 == fl) | ((f4 == 2) & (fl == 0))) and int(nf4.item()) == int(nfev.item())
+            hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, fl4, None,
+                               remote_at_ends=True, cand_ws=cws)
+            assert torch.equal(fl4, flags)
             got[row0:row0 + rows] = flags.cpu().numpy()
             assert int(nfev.item()) == int(np.count_nonzero(np.diff(rp_h[row0:row0 + rows + 1]) > 0))
         assert np.array_equal(got, ref), (graph, nshards)

@@ -30,7 +30,7 @@ for _ in range(K):
     hp.eval_sobol(it.functor, it.gset, it.tab, it.row0, it.rows, f=it.f_my, feasible=it.feas)
     ev[1].record()
     it._barrier_async()
-    hp.star_csr_local(it.row_ptr, it.col, it.row0, it.f_my, it.feas, it.is_min, it.nfev, it.off0, cand_ws=it._cand_ws)
+    hp.star_csr_local(it.row_ptr, it.col, it.row0, it.f_my, it.feas, it.is_min, it.nfev, it.off0, cand_ws=it._cand_ws, remote_at_ends=it.remote_at_ends)
     ev[2].record()
     it._barrier_wait()
     ev[3].record()
