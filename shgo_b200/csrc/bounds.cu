@@ -87,7 +87,8 @@ extern "C" int shgo_b200_local_bounds_csr(const int64_t *row_ptr, const int32_t 
 {
     SHGO_REQUIRE(d >= 1, "d must be positive (got %d)", d);
     if (m == 0) return SHGO_B200_OK;
-    SHGO_REQUIRE(row_ptr && col && x_soa && pool && lb && ub && lo && hi, "null pointer");
+    // col may be null: a graph without edges (a single isolated vertex) has no column array
+    SHGO_REQUIRE(row_ptr && x_soa && pool && lb && ub && lo && hi, "null pointer");
     uint64_t blocks = (m + 7) / 8;  // 8 warps per block
     const uint64_t cap = (uint64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;

@@ -547,6 +547,15 @@ def test_local_bounds_csr_golden(hp, name):
     assert np.array_equal(hi.cpu().numpy(), g[name + "_hi"][sub])
 
 
+def test_local_bounds_of_an_isolated_vertex(hp):
+    """shgo(..., n=1, sampling_method='simplicial'): one vertex, no edges, no column array at all"""
+    rp = torch.zeros(2, dtype=torch.int64, device="cuda")
+    col = torch.zeros(0, dtype=torch.int32, device="cuda")
+    x = torch.tensor([[0.5], [2.0]], dtype=torch.float64, device="cuda")
+    lo, hi = hp.local_bounds_csr(rp, col, x, torch.zeros(1, dtype=torch.int64, device="cuda"), [(-1, 6), (-1, 6)])
+    assert lo.cpu().tolist() == [[-1.0, -1.0]] and hi.cpu().tolist() == [[6.0, 6.0]]
+
+
 @pytest.mark.parametrize("name", [n for n in _local_bounds_names() if n.startswith(("lat2d", "lat4d"))])
 def test_lattice_local_bounds_golden(hp, name):
     """whole generations: closed form on the coordinate table == the reference walking v.nn"""
