@@ -112,3 +112,38 @@ def test_lattice_host_mirror_matches_oracle():
         assert np.array_equal(lattice.vertex_ids(p[ng:] // 2, d, gen, False), np.arange(ng, nv))
     with pytest.raises(lattice.LatticeArtefactError):
         lattice.coordinate_tables([(-3.3, 7.1)], 2)
+
+
+def test_ctypes_signatures_mirror_the_header():
+    """Every prototype of include/shgo_b200.h against the ctypes argument list the host side
+    binds: same arity, and pointer / 64-bit / 32-bit / size_t in the same positions."""
+    import ctypes
+    from shgo_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "shgo_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"SHGO_B200_API\s+([\w\s\*]+?)\b(shgo_b200_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def kind_of_c(param):
+        p = " ".join(param.split())
+        if p in ("void", ""):
+            return None
+        if "*" in p:
+            return "ptr"
+        t = p.rsplit(" ", 1)[0]
+        return {"int": "i32", "uint32_t": "u32", "uint64_t": "u64", "int64_t": "i64", "size_t": "size",
+                "double": "f64"}[t.replace("const ", "")]
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        return {ctypes.c_int: "i32", ctypes.c_uint32: "u32", ctypes.c_uint64: "u64", ctypes.c_int64: "i64",
+                ctypes.c_size_t: "size", ctypes.c_double: "f64"}[t]
+
+    for ret, name, params in protos:
+        want = [k for k in (kind_of_c(p) for p in params.split(",")) if k]
+        restype, argtypes = _lib.SIGNATURES[name]
+        got = [kind_of_ctypes(t) for t in argtypes]
+        # size_t and uint64_t are the same machine type; the binding may use either
+        norm = lambda ks: ["u64" if k == "size" else k for k in ks]
+        assert norm(got) == norm(want), (name, got, want)
