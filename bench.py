@@ -28,7 +28,7 @@ D = 8
 BOUNDS = [(-5.0, 5.0)] * D
 FUNCTOR = "styblinski_tang"
 FLOPS_PER_POINT = 2 * D + 7 * D + 1      # scaling 2d + functor 7d+1
-KERNELS_PER_STEP = 5                      # eval, star(+nfev), 3x compaction (+4 at N>1: candidates, remote)
+KERNELS_PER_STEP = 5                      # eval, star(+nfev), 3x compaction (+1 at N>1: the phase-2 kernel)
 
 
 def parse():
@@ -404,7 +404,7 @@ def main():
                         "frac_fp64": eval_tflops / fp64_peak if fp64_peak else None,
                         "hbm_write_gbs": 9 * rows / (eval_ms * 1e-3) / 1e9},
         "pool_size": int(pc[0].item()), "nfev": int(pc[1].item()),
-        "gpu_launches": (KERNELS_PER_STEP + (4 if world > 1 and args.exchange == "p2p" else 0)) * args.steps,
+        "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 and args.exchange == "p2p" else 0)) * args.steps,
         "clocks": clocks,
     }
     if e2e:
