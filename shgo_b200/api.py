@@ -118,27 +118,20 @@ class DeviceSobolSampler:
         return u
 
 
-def _make(driver_mod, func, bounds, args, constraints, n, iters, callback, minimizer_kwargs, options,
-          sampling_method, workers):
-    sampler = None
-    if sampling_method == "sobol":
-        # the driver rounds n up to a power of two for its own Sobol engine (_shgo.py:696-697);
-        # a callable sampler bypasses that, so do it here
-        nn = 100 if n is None else n
-        n = int(2 ** np.ceil(np.log2(nn)))
-        b = np.array(bounds, float) if not hasattr(bounds, "lb") else np.stack([bounds.lb, bounds.ub], 1)
-        b = b.copy()
-        b[~np.isfinite(b[:, 0]), 0] = -1e50
-        b[~np.isfinite(b[:, 1]), 1] = 1e50
-        sampler = DeviceSobolSampler(b.shape[0], b)
-        sampling_method = sampler
-    s = driver_mod.SHGO(func, bounds, args=args, constraints=constraints, n=n, iters=iters,
-                        callback=callback, minimizer_kwargs=minimizer_kwargs, options=options,
-                        sampling_method=sampling_method, workers=workers)
-    if sampler is not None:
-        s.HC._sampler = sampler
-        s.sampling_method = "sobol"       # only read by minimize() to pick the local-bounds rule
-    return s
+def _device_sampler(n, bounds, sampling_method):
+    """(n, sampling_method, sampler) with 'sobol' replaced by the device generator."""
+    if sampling_method != "sobol":
+        return n, sampling_method, None
+    # the driver rounds n up to a power of two for its own Sobol engine (_shgo.py:696-697);
+    # a callable sampler bypasses that, so do it here
+    nn = 100 if n is None else n
+    n = int(2 ** np.ceil(np.log2(nn)))
+    b = np.array(bounds, float) if not hasattr(bounds, "lb") else np.stack([bounds.lb, bounds.ub], 1)
+    b = b.copy()
+    b[~np.isfinite(b[:, 0]), 0] = -1e50
+    b[~np.isfinite(b[:, 1]), 1] = 1e50
+    sampler = DeviceSobolSampler(b.shape[0], b)
+    return n, sampler, sampler
 
 
 def SHGO(func, bounds, args=(), constraints=None, n=None, iters=None, callback=None,
@@ -146,37 +139,27 @@ def SHGO(func, bounds, args=(), constraints=None, n=None, iters=None, callback=N
     """The driver's SHGO object (same constructor as shgo/_shgo.py:491) with ``HC`` on the device.
     Use it like the reference's: ``s.iterate_all()``, ``s.iterate()``, ``s.res`` ..."""
     m = install(driver)
-    return _make(m, func, bounds, args, constraints, n, iters, callback, minimizer_kwargs, options,
-                 sampling_method, workers)
+    n, sampling_method, sampler = _device_sampler(n, bounds, sampling_method)
+    _cx.set_pending_sampler(sampler)          # picked up by the DeviceComplex the driver constructs
+    try:
+        return m.SHGO(func, bounds, args=args, constraints=constraints, n=n, iters=iters, callback=callback,
+                      minimizer_kwargs=minimizer_kwargs, options=options, sampling_method=sampling_method,
+                      workers=workers)
+    finally:
+        _cx.set_pending_sampler(None)
 
 
 def shgo(func, bounds, args=(), constraints=None, n=100, iters=1, callback=None,
          minimizer_kwargs=None, options=None, sampling_method="simplicial", *, workers=1, driver=None):
     """Drop-in for the reference's ``shgo()`` (shgo/_shgo.py:22-487): same arguments, same
-    OptimizeResult fields.  The body below is the reference's own epilogue (_shgo.py:447-487)."""
+    OptimizeResult fields.  It IS the driver's own ``shgo()``, run while ``Complex`` is bound to
+    DeviceComplex; only ``sampling_method='sobol'`` is rerouted to the device generator."""
     with _installed(driver) as m:
-        if hasattr(bounds, "lb") and hasattr(bounds, "ub"):      # scipy.optimize.Bounds
-            bounds = np.stack([np.asarray(bounds.lb, float), np.asarray(bounds.ub, float)], 1).tolist()
-        s = _make(m, func, bounds, args, constraints, n, iters, callback, minimizer_kwargs, options,
-                  sampling_method, workers)
-        s.iterate_all()
-        if not s.break_routine:
-            if s.disp:
-                import logging
-                logging.info("Successfully completed construction of complex.")
-        if len(s.LMC.xl_maps) == 0:
-            # no minimiser found: report the lowest sampled vertex (_shgo.py:466-476)
-            s.find_lowest_vertex()
-            s.break_routine = True
-            s.fail_routine(mes="Failed to find a feasible minimizer point. "
-                               f"Lowest sampling point = {s.f_lowest}")
-            s.res.fun = s.f_lowest
-            s.res.x = s.x_lowest
-            s.res.nfev = s.fn
-            s.res.tnev = s.n_sampled
-        else:
-            pass
-        if not s.break_routine:
-            s.res.message = "Optimization terminated successfully."
-            s.res.success = True
-        return s.res
+        n, sampling_method, sampler = _device_sampler(n, bounds, sampling_method)
+        _cx.set_pending_sampler(sampler)
+        try:
+            return m.shgo(func, bounds, args=args, constraints=constraints, n=n, iters=iters,
+                          callback=callback, minimizer_kwargs=minimizer_kwargs, options=options,
+                          sampling_method=sampling_method, workers=workers)
+        finally:
+            _cx.set_pending_sampler(None)

@@ -42,6 +42,7 @@ There is no CPU implementation of the classification: without the CUDA library t
 """
 import collections
 import importlib
+import threading
 
 import numpy as np
 import torch
@@ -49,6 +50,15 @@ import torch
 from . import functors as F
 from . import hotpath as hp
 from . import lattice as lat
+
+
+_PENDING = threading.local()
+
+
+def set_pending_sampler(sampler):
+    """Hand the device Sobol sampler of an upcoming driver call to the DeviceComplex that call will
+    construct (the driver builds `HC` itself, _shgo.py:680-684)."""
+    _PENDING.sampler = sampler
 
 
 def torch_vectorized(fn):
@@ -276,7 +286,8 @@ class DeviceComplex:
         self._host_values = {}       # host-callable route: coordinates -> (f, feasible)
         self._rank = None            # mesh: insertion rank of every vertex in the reference's cache
         self._mesh_calls = 0
-        self._sampler = None
+        self._sampler = getattr(_PENDING, "sampler", None)   # consumed: one complex per driver call
+        _PENDING.sampler = None
         self._ref = None             # driver-side Python Complex used as a graph generator
         self._ref_keys = []
         self._lcb, self._lcb_key, self._x_soa = {}, None, None
