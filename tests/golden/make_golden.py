@@ -203,6 +203,10 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["local_bounds"]:      # fixtures are independent: regenerate just this one
         local_bounds_cases()
         sys.exit(0)
+    if sys.argv[1:] == ["lattice_high_d"]:
+        lattice_case("lattice_unit_6d", [(0.0, 1.0)] * 6, 1)
+        lattice_case("lattice_unit_7d", [(0.0, 1.0)] * 7, 1)
+        sys.exit(0)
     B512 = [(-5.12, 5.12)]
     sobol_case("sobol_rastrigin_6d_256", "rastrigin", None, B512 * 6, 256, full_simplices=False)
     sobol_case("sobol_rastrigin_3d_4096", "rastrigin", None, B512 * 3, 4096)
@@ -225,6 +229,8 @@ if __name__ == "__main__":
     lattice_case("lattice_ackley_3d", [(-32.768, 32.768)] * 3, 2)
     lattice_case("lattice_mixed_3d", [(-3.3, 7.1), (0.0, 2.0), (-5.0, 5.0)], 2)
     lattice_case("lattice_unit_1d", [(0.0, 1.0)], 3)
+    lattice_case("lattice_unit_6d", [(0.0, 1.0)] * 6, 1)       # 793 / 18 928
+    lattice_case("lattice_unit_7d", [(0.0, 1.0)] * 7, 1)       # 2315 / 92 194
 
     simplicial_pools_case("simplicial_ackley_3d_it3", "ackley", None, [(-32.768, 32.768)] * 3, 3)
     simplicial_pools_case("simplicial_rastrigin_2d_it4", "rastrigin", None, B512 * 2, 4)

@@ -5,7 +5,8 @@ CPU only.  This is what makes the oracle trustworthy as the checker of the CUDA 
 import numpy as np
 import pytest
 
-from conftest import (BIT_EXACT_F, LATTICE_CASES, SIMPLICIAL_POOL_CASES, SOBOL_CASES, gset_of,
+from conftest import (BIT_EXACT_F, LATTICE_CASES, LATTICE_CASES_HIGH_D, SIMPLICIAL_POOL_CASES, SOBOL_CASES,
+                      gset_of,
                       load_golden)
 from oracle import oracle as orc
 
@@ -69,7 +70,7 @@ def test_sobol_case(name):
     assert orc.nfev(row_ptr, feas) == int(g["nfev"])
 
 
-@pytest.mark.parametrize("name", LATTICE_CASES)
+@pytest.mark.parametrize("name", LATTICE_CASES + LATTICE_CASES_HIGH_D)
 def test_lattice_case(name):
     g = load_golden(name)
     bounds = [tuple(b) for b in g["bounds"]]
