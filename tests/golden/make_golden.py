@@ -203,6 +203,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["local_bounds"]:      # fixtures are independent: regenerate just this one
         local_bounds_cases()
         sys.exit(0)
+    if sys.argv[1:] == ["simplicial_10d"]:    # ten minutes: the reference builds 10-D generation 1
+        simplicial_pools_case("simplicial_ackley_10d_it2", "ackley", None, [(-32.768, 32.768)] * 10, 2)
+        sys.exit(0)
     if sys.argv[1:] == ["lattice_high_d"]:
         lattice_case("lattice_unit_6d", [(0.0, 1.0)] * 6, 1)
         lattice_case("lattice_unit_7d", [(0.0, 1.0)] * 7, 1)
@@ -238,5 +241,6 @@ if __name__ == "__main__":
                           [(-5, 5)] * 4, 3)
     simplicial_pools_case("simplicial_sphere_2d_cons_it3", "sphere", "sum_le_6",
                           [(-1, 6)] * 2, 3)
+    simplicial_pools_case("simplicial_ackley_10d_it2", "ackley", None, [(-32.768, 32.768)] * 10, 2)
     end_to_end()
     local_bounds_cases()

@@ -5,8 +5,8 @@ CPU only.  This is what makes the oracle trustworthy as the checker of the CUDA 
 import numpy as np
 import pytest
 
-from conftest import (BIT_EXACT_F, LATTICE_CASES, LATTICE_CASES_HIGH_D, SIMPLICIAL_POOL_CASES, SOBOL_CASES,
-                      gset_of,
+from conftest import (BIT_EXACT_F, LATTICE_CASES, LATTICE_CASES_HIGH_D, SIMPLICIAL_POOL_CASES,
+                      SIMPLICIAL_POOL_CASES_HIGH_D, SOBOL_CASES, gset_of,
                       load_golden)
 from oracle import oracle as orc
 
@@ -98,7 +98,7 @@ def test_lattice_float_artefact_is_detectable():
     assert len(g["coords_g1"]) == 40 and orc.lattice_nvert(3, 1)[0] == 35
 
 
-@pytest.mark.parametrize("name", SIMPLICIAL_POOL_CASES)
+@pytest.mark.parametrize("name", SIMPLICIAL_POOL_CASES + SIMPLICIAL_POOL_CASES_HIGH_D)
 def test_simplicial_pools(name):
     """pool_k = strict star minima of generation k minus every earlier local-search start
     vertex (the star() self-loop quirk, _shgo.py:1027-1032 / SURVEY row a6)."""
