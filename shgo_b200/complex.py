@@ -300,12 +300,11 @@ class DeviceComplex:
     # =====================================================================================
     def refine_all(self, centroids=True):
         """One whole generation (Complex.refine_all / triangulate, _complex.py:514-533,359)."""
-        if self.mode in (None, "lattice") and self.symmetry is None:
-            self._enter_lattice(self._lat_gen + 1)
-        else:
-            self._ensure_hostgraph()
-            self._ref.refine_all()
-            self._sync_hostgraph()
+        if self.mode in (None, "lattice") and self.symmetry is None and self._enter_lattice(self._lat_gen + 1):
+            return
+        self._ensure_hostgraph()
+        self._ref.refine_all()
+        self._sync_hostgraph()
 
     def refine(self, n=1):
         """Add ~n vertices (Complex.refine, _complex.py:474-512).  Completing generation 0 from
@@ -313,8 +312,8 @@ class DeviceComplex:
         driver-side Python generator (graph only), then evaluated / classified on the device."""
         if n is None:
             return self.refine_all()
-        if self.mode is None and self.symmetry is None and n == 2 ** self.dim + 1:
-            return self._enter_lattice(0)
+        if self.mode is None and self.symmetry is None and n == 2 ** self.dim + 1 and self._enter_lattice(0):
+            return
         self._ensure_hostgraph()
         self._ref.refine(n)
         self._sync_hostgraph()
@@ -380,8 +379,17 @@ class DeviceComplex:
 
     # ---- lattice ---------------------------------------------------------------------------
     def _enter_lattice(self, gen):
+        """Switch to generation `gen` of the closed-form complex; False when the closed form does
+        not describe what the reference builds for these bounds (fp64 midpoints that depend on the
+        split direction make it create near-duplicate vertices, SURVEY.md section 7 hard part 6):
+        the caller then replays the reference's own generator (hostgraph) so that the result stays
+        identical to the reference's, duplicates included."""
+        try:
+            tab = lat.coordinate_tables(self.bounds, gen)
+        except lat.LatticeArtefactError:
+            return False
         self.mode = "lattice"
-        self._tab_host = lat.coordinate_tables(self.bounds, gen)   # raises on fp64 artefact bounds
+        self._tab_host = tab
         self._tab = torch.from_numpy(self._tab_host).to(self.device)
         self._lat_gen = gen
         self.gen = gen
@@ -389,6 +397,7 @@ class DeviceComplex:
         if self._n >= 2 ** 32:
             raise MemoryError("generation %d of a %d-D lattice has %d vertices" % (gen, self.dim, self._n))
         self._dirty = True
+        return True
 
     def _process_lattice(self):
         d, gen, n = self.dim, self._lat_gen, self._n

@@ -18,8 +18,8 @@ import numpy as np
 
 class LatticeArtefactError(ValueError):
     """Bounds for which the REFERENCE itself builds near-duplicate vertices (the fp64 midpoint of
-    an edge depends on the direction it is split from, SURVEY.md section 7 hard part 6); parity
-    with it is undefined there, so the device path refuses instead of guessing."""
+    an edge depends on the direction it is split from, SURVEY.md section 7 hard part 6): the closed
+    form does not apply; DeviceComplex then runs the reference's own generator for the graph."""
 
 
 def coordinate_tables(bounds, gen, check=True):
