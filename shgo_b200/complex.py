@@ -233,6 +233,14 @@ class DeviceVertexCache:
 
     def _mark_started(self, v):
         self._started.add(self._c._stable_key(v))
+        # The reference's star() really inserts v into v.nn, and its generators walk nn sets
+        # (`for v in vo.nn: v.connect(vc)`): the self-loop changes which edges later refinements
+        # create.  The driver-side generator of the hostgraph route must see the same loop.
+        ref = self._c._ref
+        if ref is not None:
+            rv = ref.V.cache.get(v.x)
+            if rv is not None:
+                rv.nn.add(rv)
 
 
 class DeviceComplex:
@@ -331,8 +339,18 @@ class DeviceComplex:
         simp = np.ascontiguousarray(simplices)
         if simp.ndim != 2 or simp.shape[0] == 0:
             simp = np.zeros((0, 2), np.int32)
-        n = pts.shape[0]
         simp = simp.astype(np.int32, copy=False)
+        # The reference's vertices are keyed by coordinates and connect() only ever adds: a second
+        # mesh is merged into the first.  When the new point array extends the old one (qhull in
+        # incremental mode: Tri.points grows) indices persist and nothing has to be done; otherwise
+        # (1-D meshes and non-incremental qhull hand over the fresh points only) the new points
+        # are appended behind the old ones and the simplices re-indexed.
+        if self._points_host is not None and self._n > 0:
+            old = self._points_host
+            if not (pts.shape[0] >= old.shape[0] and np.array_equal(pts[:old.shape[0]], old)):
+                simp = (simp + old.shape[0]).astype(np.int32)
+                pts = np.ascontiguousarray(np.concatenate([old, pts]))
+        n = pts.shape[0]
         # vertices are keyed by coordinate tuple in the reference: coincident points are ONE vertex
         # (points of the unscrambled Sobol sequence are pairwise distinct: no need to look)
         canon = None if self._sampler_tables_if_points_are_sobol(pts) is not None else self._coincident_map(pts)
@@ -527,6 +545,11 @@ class DeviceComplex:
         if self.argmin_index >= 0:
             want = np.union1d(pool, [self.argmin_index])
         want = np.asarray(want, np.int64)
+        if self.mode == "lattice" and len(want) > 1:
+            # list the vertices in the reference's cache order as far as it is known in closed form
+            # (older generation first; generation 0 exactly): X_min / minimizer_pool inherit it
+            first, sec = lat.insertion_key(want, self.dim, self._lat_gen)
+            want = want[np.lexsort((sec, first))]
         if self.mode == "mesh" and self._rank is not None and len(want) > 1:
             # list the vertices in the reference's cache order: SHGO.minimizers builds X_min in
             # that order and minimise_pool starts from X_min[0] (_shgo.py:1146-1152,1177)
@@ -663,6 +686,12 @@ class DeviceComplex:
                 self._ref.refine_all()
             for v in self._ref.V.cache.values():
                 v.check_min = False
+            # star() calls made so far (see DeviceVertexCache._mark_started): whole generations are
+            # not affected by the self-loops (verified against the reference), what follows is
+            for key in self.V._started:
+                rv = self._ref.V.cache.get(key)
+                if rv is not None:
+                    rv.nn.add(rv)
         self.mode = "hostgraph"
         self._ref_keys = []
 
@@ -674,13 +703,15 @@ class DeviceComplex:
         self._ref_keys = keys
         n = len(keys)
         index = {k: i for i, k in enumerate(keys)}
-        deg = np.fromiter((len(v.nn) for v in cache.values()), np.int64, n)
+        # self-loops (mirrored star() calls) are not edges of the graph that is classified: their
+        # effect on minimiser() is what _started / _excluded track
+        deg = np.fromiter((len(v.nn) - (v in v.nn) for v in cache.values()), np.int64, n)
         rp = np.zeros(n + 1, np.int64)
         np.cumsum(deg, out=rp[1:])
         col = np.empty(max(int(rp[-1]), 1), np.int32)
         for i, v in enumerate(cache.values()):
             if deg[i]:
-                col[rp[i]:rp[i + 1]] = sorted(index[w.x] for w in v.nn)
+                col[rp[i]:rp[i + 1]] = sorted(index[w.x] for w in v.nn if w is not v)
         col = col[: int(rp[-1])]
         self._points_host = np.array(keys, np.float64).reshape(n, self.dim)
         self._x_soa = None

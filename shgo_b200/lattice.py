@@ -74,6 +74,39 @@ def decode(ids, d, gen):
     return p
 
 
+def insertion_key(ids, d, gen):
+    """Sort key that lists vertices the way the reference's vertex cache holds them, as far as that
+    has a closed form.  The cache is append-only, so a vertex created in an earlier generation
+    precedes every vertex of a later one; generation 0 is created as origin, supremum, the other
+    corners in binary counting order with axis 0 fastest, centroid last (_complex.py:192-357).
+    Within a later generation the reference's order is that of its nested generators and has no
+    closed form: ids are used there.  Returns (first generation, secondary key), both int64."""
+    p = decode(ids, d, gen)                       # lattice indices at resolution L = 2^(gen+1)
+    L = 1 << (gen + 1)
+    # trailing zeros of every coordinate (index 0 counts as "as many as needed")
+    tz = np.full(p.shape, gen + 2, np.int64)
+    nz = p != 0
+    tz[nz] = np.log2(p[nz] & -p[nz]).astype(np.int64)
+    m = tz.min(axis=-1)
+    same = np.all(tz == m[..., None], axis=-1)    # odd multiples of 2^m on every axis: a centroid of generation gen - m
+    first = np.where(same, gen - m, gen + 1 - m)
+    first = np.clip(first, 0, gen)
+    ids = np.asarray(ids, np.int64)
+    sec = ids.copy()
+    g0 = first == 0
+    if g0.any():
+        q = p[g0]
+        corner = np.all((q == 0) | (q == L), axis=-1)
+        bits = (q == L).astype(np.int64)
+        count = (bits << np.arange(d, dtype=np.int64)).sum(-1)
+        key = count + 1                           # binary counting, axis 0 fastest
+        key[np.all(q == 0, axis=-1)] = 0          # origin
+        key[np.all(q == L, axis=-1)] = 1          # supremum
+        key[~corner] = (1 << d) + 2               # the centroid
+        sec[g0] = key
+    return first, sec
+
+
 def neighbours(vid, d, gen):
     """Neighbour ids of one vertex by the parity rule (used only to materialise the few vertex
     objects the driver touches: pool members and their stars)."""

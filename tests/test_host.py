@@ -147,3 +147,30 @@ def test_ctypes_signatures_mirror_the_header():
         # size_t and uint64_t are the same machine type; the binding may use either
         norm = lambda ks: ["u64" if k == "size" else k for k in ks]
         assert norm(got) == norm(want), (name, got, want)
+
+
+@pytest.mark.parametrize("name", ["lattice_unit_1d", "lattice_unit_2d", "lattice_unit_3d", "lattice_rastrigin_4d",
+                                  "lattice_rosen_5d", "lattice_unit_6d"])
+def test_lattice_insertion_key_against_the_reference_cache_order(name):
+    """The fixtures list the vertices in the reference's cache order, generation after generation:
+    the closed-form key must give every vertex the generation it was created in and reproduce the
+    order of generation 0 exactly (that is the part of X_min's order that has a closed form)."""
+    from conftest import load_golden
+    from shgo_b200 import lattice
+    g = load_golden(name)
+    bounds = [tuple(b) for b in g["bounds"]]
+    d = len(bounds)
+    born = {}
+    for gen in range(int(g["gens"]) + 1):
+        coords = g[f"coords_g{gen}"]
+        for c in coords:
+            born.setdefault(tuple(c), gen)
+        tab = lattice.coordinate_tables(bounds, gen)
+        P = np.stack([np.searchsorted(tab[i], coords[:, i]) for i in range(d)], 1)
+        assert all(np.array_equal(tab[i][P[:, i]], coords[:, i]) for i in range(d))
+        grid = np.all(P % 2 == 0, axis=1)
+        ids = np.where(grid, lattice.vertex_ids(P // 2, d, gen, True), lattice.vertex_ids((P - 1) // 2, d, gen, False))
+        first, sec = lattice.insertion_key(ids, d, gen)
+        assert np.array_equal(first, [born[tuple(c)] for c in coords]), (name, gen)
+        g0 = first == 0
+        assert np.array_equal(np.argsort(sec[g0], kind="stable"), np.arange(int(g0.sum()))), (name, gen)

@@ -196,3 +196,26 @@ def test_coincident_points_merge_like_the_reference(sb):
     for v in dev.V.cache.values():            # neighbour sets, by coordinates
         if v.minimiser():
             assert {w.x for w in v.nn} == {w.x for w in ref.V[v.x].nn}
+
+
+REGRESSIONS = [
+    # 1-D meshes: every iteration hands over only its fresh points (driver: Tri = (C, edges))
+    ("rastrigin", [(-2.1, 4.4)], dict(sampling_method="sobol", n=94, iters=2)),
+    ("styblinski_tang", [(-2.0, 6.2)], dict(sampling_method="halton", n=86, iters=2)),
+    # the reference's star() self-loop changes the edges later partial refinements create
+    ("ackley", [(-6.0, -2.73), (-4.0, -2.13)], dict(sampling_method="simplicial", n=40, iters=3)),
+    # the literal default call with several iterations: generation 0 in closed form, then partial
+    ("rastrigin", [(-5.12, 4.0)] * 2, dict(sampling_method="simplicial", n=5, iters=4)),
+    ("styblinski_tang", [(-5.0, 4.0)] * 3, dict(sampling_method="simplicial", n=9, iters=3)),
+    ("ackley", [(-20.0, 32.768)] * 4, dict(sampling_method="simplicial", iters=2)),
+]
+
+
+@pytest.mark.parametrize("fname,bounds,kw", REGRESSIONS)
+def test_cases_found_by_the_differential_fuzz(sb, fname, bounds, kw):
+    from shgo_b200 import functors as F
+    fn = getattr(F, fname)
+    ref = _reference_run(fn, bounds, **kw)
+    res = sb.shgo(fn, bounds, **kw)
+    assert (res.success, res.nfev, res.nit, len(res.funl)) == (ref.success, ref.nfev, ref.nit, len(ref.funl))
+    np.testing.assert_allclose(np.sort(res.funl), np.sort(ref.funl), rtol=1e-6, atol=1e-8)
