@@ -678,7 +678,10 @@ class DeviceComplex:
         RefComplex = _driver_complex_class()
         # field-less in effect: the dummy field is never evaluated (process_pools is never called
         # on it); it only makes the generator create vertices that carry check_min flags
-        self._ref = RefComplex(self.dim, domain=self.bounds, sfield=_never_called, symmetry=self.symmetry)
+        # the driver's own `domain` object, not a normalised copy: with `symmetry` the reference's
+        # triangulate() edits a copy of the bounds in place and behaves differently for an ndarray
+        # (what the driver passes) than for a list of pairs
+        self._ref = RefComplex(self.dim, domain=self.domain, sfield=_never_called, symmetry=self.symmetry)
         if self.mode == "lattice":
             # replay the whole generations already built, then continue step-wise
             self._ref.refine(None)

@@ -208,6 +208,9 @@ REGRESSIONS = [
     ("rastrigin", [(-5.12, 4.0)] * 2, dict(sampling_method="simplicial", n=5, iters=4)),
     ("styblinski_tang", [(-5.0, 4.0)] * 3, dict(sampling_method="simplicial", n=9, iters=3)),
     ("ackley", [(-20.0, 32.768)] * 4, dict(sampling_method="simplicial", iters=2)),
+    # options['symmetry']: the generator must get the driver's own ndarray of bounds
+    ("sphere", [(-4.04, 4.46), (-1.59, 5.91), (-0.93, 2.57), (-4.07, 3.43)],
+     dict(sampling_method="simplicial", n=6, iters=2, options={"symmetry": True})),
 ]
 
 

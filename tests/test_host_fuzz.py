@@ -1,9 +1,12 @@
 """Randomised differential test of the host logic: `shgo_b200.shgo` (DeviceComplex, kernels replaced
 by the oracle-backed stand-in) against the driver with its own Python Complex on random problems
 -- dimensions 1-4, uneven bounds, every sampling method, partial and whole generations, several
-iterations, constraints, driver options.  Found in round 1: 1-D meshes hand over only the fresh
+iterations, inequality and equality constraints, objective arguments, driver options (local_iter,
+minimize_every_iter, maxfev / maxev / maxiter, infty_constraints, symmetry), local minimisers.
+Found in round 1: 1-D meshes hand over only the fresh
 points of an iteration; the reference's star() self-loops change which edges later partial
-refinements create.
+refinements create; with `symmetry` the reference's triangulate() behaves differently for an ndarray
+of bounds than for a list of pairs.
 
 Known, documented deviation that is excluded here: `local_iter` on whole generations (n=None) starts
 its local searches from X_min[0], the pool vertex the reference's cache created first; inside one
@@ -18,13 +21,17 @@ def _pyfun(x):
     return float(np.sum((x - 0.3) ** 2) + np.sin(3 * x[0]))
 
 
+def _pyargs(x, a, b):
+    return float(np.sum((x - a) ** 2) * b)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
 def test_random_problems_match_the_driver_with_its_python_complex(monkeypatch, seed):
     fake_hotpath.install(monkeypatch)
     import shgo_b200
     from shgo_b200 import api, functors as F
     m = api.driver_module()
-    funs = [F.rastrigin, F.ackley, F.styblinski_tang, F.sphere, _pyfun, F.rosenbrock]
+    funs = [F.rastrigin, F.ackley, F.styblinski_tang, F.sphere, _pyfun, F.rosenbrock, _pyargs]
     rng = np.random.default_rng(1000 + seed)
     for trial in range(25):
         d = int(rng.integers(1, 5))
@@ -36,6 +43,8 @@ def test_random_problems_match_the_driver_with_its_python_complex(monkeypatch, s
         bounds = list(zip(lo.tolist(), hi.tolist()))
         method = ["simplicial", "sobol", "halton"][int(rng.integers(0, 3))]
         kw = dict(sampling_method=method)
+        if fn is _pyargs:
+            kw["args"] = (float(rng.uniform(-1, 1)), 2.0)
         if method == "simplicial":
             kw["n"] = [None, int(rng.integers(1, 60)), 2 ** d + 1][int(rng.integers(0, 3))]
             kw["iters"] = int(rng.integers(1, 4)) if d <= 3 else int(rng.integers(1, 3))
@@ -49,16 +58,31 @@ def test_random_problems_match_the_driver_with_its_python_complex(monkeypatch, s
             opts["local_iter"] = int(rng.integers(1, 4))
         if rng.random() < 0.2:
             opts["maxfev"] = int(rng.integers(5, 200))
+        if rng.random() < 0.15:
+            opts["maxev"] = int(rng.integers(5, 200))
+        if rng.random() < 0.15:
+            opts["maxiter"] = int(rng.integers(1, 4))
+        if rng.random() < 0.15:
+            opts["infty_constraints"] = False
+        if rng.random() < 0.1 and method == "simplicial":
+            opts["symmetry"] = True
         if opts:
             kw["options"] = opts
+        if rng.random() < 0.15:
+            kw["minimizer_kwargs"] = {"method": ["SLSQP", "COBYLA", "L-BFGS-B"][int(rng.integers(0, 3))]}
         cons = None
-        if rng.random() < 0.3 and d >= 2:
+        r = rng.random()
+        if r < 0.25 and d >= 2:
             c = float(rng.uniform(-2, 6))
-            cons = ({"type": "ineq", "fun": lambda x, c=c: c - x[0] - x[1]},)
+            cons = ({"type": "ineq", "fun": lambda x, *a, c=c: c - x[0] - x[1]},)
+        elif r < 0.35 and d >= 2:
+            c = float(rng.uniform(-2, 6))
+            cons = ({"type": "ineq", "fun": lambda x, *a, c=c: c - x[0] - x[1]},
+                    {"type": "eq", "fun": lambda x, *a: x[0] - x[1]})
         ref = m.shgo(fn, bounds, constraints=cons, **kw)
         res = shgo_b200.shgo(fn, bounds, constraints=cons, **kw)
         what = (seed, trial, getattr(fn, "__name__", "?"), bounds, kw, cons is not None)
-        assert (res.success, res.nfev, res.nit) == (ref.success, ref.nfev, ref.nit), what
+        assert (res.success, res.nfev, res.nit, res.message) == (ref.success, ref.nfev, ref.nit, ref.message), what
         a, b = np.sort(np.atleast_1d(getattr(res, "funl", []))), np.sort(np.atleast_1d(getattr(ref, "funl", [])))
         assert len(a) == len(b), what
         np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-8, err_msg=str(what))
