@@ -134,13 +134,21 @@ def _device_sampler(n, bounds, sampling_method):
     return n, sampler, sampler
 
 
+def _needs_cache_order(options, sampling_method):
+    """options['local_iter'] starts its local searches from X_min[0], the pool vertex the reference's
+    cache created first (_shgo.py:1177); on the simplicial complex that order has a closed form only
+    across generations, so such a call gets its graph from the reference's generator."""
+    return bool(options and options.get("local_iter")) and sampling_method == "simplicial"
+
+
 def SHGO(func, bounds, args=(), constraints=None, n=None, iters=None, callback=None,
          minimizer_kwargs=None, options=None, sampling_method="simplicial", workers=1, driver=None):
     """The driver's SHGO object (same constructor as shgo/_shgo.py:491) with ``HC`` on the device.
     Use it like the reference's: ``s.iterate_all()``, ``s.iterate()``, ``s.res`` ..."""
     m = install(driver)
     n, sampling_method, sampler = _device_sampler(n, bounds, sampling_method)
-    _cx.set_pending_sampler(sampler)          # picked up by the DeviceComplex the driver constructs
+    # picked up by the DeviceComplex the driver constructs
+    _cx.set_pending_sampler(sampler, _needs_cache_order(options, sampling_method))
     try:
         return m.SHGO(func, bounds, args=args, constraints=constraints, n=n, iters=iters, callback=callback,
                       minimizer_kwargs=minimizer_kwargs, options=options, sampling_method=sampling_method,
@@ -156,7 +164,7 @@ def shgo(func, bounds, args=(), constraints=None, n=100, iters=1, callback=None,
     DeviceComplex; only ``sampling_method='sobol'`` is rerouted to the device generator."""
     with _installed(driver) as m:
         n, sampling_method, sampler = _device_sampler(n, bounds, sampling_method)
-        _cx.set_pending_sampler(sampler)
+        _cx.set_pending_sampler(sampler, _needs_cache_order(options, sampling_method))
         try:
             return m.shgo(func, bounds, args=args, constraints=constraints, n=n, iters=iters,
                           callback=callback, minimizer_kwargs=minimizer_kwargs, options=options,

@@ -55,10 +55,13 @@ from . import lattice as lat
 _PENDING = threading.local()
 
 
-def set_pending_sampler(sampler):
+def set_pending_sampler(sampler, exact_cache_order=False):
     """Hand the device Sobol sampler of an upcoming driver call to the DeviceComplex that call will
-    construct (the driver builds `HC` itself, _shgo.py:680-684)."""
+    construct (the driver builds `HC` itself, _shgo.py:680-684).  exact_cache_order: the call uses
+    options['local_iter'], whose result depends on the order in which the reference's cache created
+    the vertices of one generation -- that complex takes its graph from the reference's generator."""
     _PENDING.sampler = sampler
+    _PENDING.exact_cache_order = bool(exact_cache_order)
 
 
 def torch_vectorized(fn):
@@ -295,7 +298,8 @@ class DeviceComplex:
         self._rank = None            # mesh: insertion rank of every vertex in the reference's cache
         self._mesh_calls = 0
         self._sampler = getattr(_PENDING, "sampler", None)   # consumed: one complex per driver call
-        _PENDING.sampler = None
+        self._exact_cache_order = getattr(_PENDING, "exact_cache_order", False)
+        _PENDING.sampler, _PENDING.exact_cache_order = None, False
         self._ref = None             # driver-side Python Complex used as a graph generator
         self._ref_keys = []
         self._lcb, self._lcb_key, self._x_soa = {}, None, None
@@ -308,7 +312,8 @@ class DeviceComplex:
     # =====================================================================================
     def refine_all(self, centroids=True):
         """One whole generation (Complex.refine_all / triangulate, _complex.py:514-533,359)."""
-        if self.mode in (None, "lattice") and self.symmetry is None and self._enter_lattice(self._lat_gen + 1):
+        if (self.mode in (None, "lattice") and self.symmetry is None and not self._exact_cache_order
+                and self._enter_lattice(self._lat_gen + 1)):
             return
         self._ensure_hostgraph()
         self._ref.refine_all()
@@ -320,7 +325,8 @@ class DeviceComplex:
         driver-side Python generator (graph only), then evaluated / classified on the device."""
         if n is None:
             return self.refine_all()
-        if self.mode is None and self.symmetry is None and n == 2 ** self.dim + 1 and self._enter_lattice(0):
+        if (self.mode is None and self.symmetry is None and n == 2 ** self.dim + 1
+                and not self._exact_cache_order and self._enter_lattice(0)):
             return
         self._ensure_hostgraph()
         self._ref.refine(n)

@@ -8,9 +8,9 @@ points of an iteration; the reference's star() self-loops change which edges lat
 refinements create; with `symmetry` the reference's triangulate() behaves differently for an ndarray
 of bounds than for a list of pairs.
 
-Known, documented deviation that is excluded here: `local_iter` on whole generations (n=None) starts
-its local searches from X_min[0], the pool vertex the reference's cache created first; inside one
-generation that order has no closed form."""
+`local_iter` starts its local searches from X_min[0], the pool vertex the reference's cache created
+first; inside one whole generation that order has no closed form, so `shgo_b200.shgo` / `SHGO` give
+such calls their graph from the reference's generator."""
 import numpy as np
 import pytest
 
@@ -54,7 +54,7 @@ def test_random_problems_match_the_driver_with_its_python_complex(monkeypatch, s
         opts = {}
         if rng.random() < 0.3:
             opts["minimize_every_iter"] = bool(rng.integers(0, 2))
-        if rng.random() < 0.3 and not (method == "simplicial" and kw["n"] is None):
+        if rng.random() < 0.3:
             opts["local_iter"] = int(rng.integers(1, 4))
         if rng.random() < 0.2:
             opts["maxfev"] = int(rng.integers(5, 200))
