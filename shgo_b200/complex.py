@@ -283,8 +283,9 @@ class DeviceComplex:
         # evaluation route
         self._fid = F.functor_id(sfield) if not self.sfield_args else None
         self._gid = F.constraint_set_id(self.g_cons, self.g_args)
-        if self._fid is not None and self._gid is None:
-            self._fid = None        # objective registered but constraints are not: generic route
+        if self._fid is not None and not F.supports(self._fid, self._gid, self.dim):
+            # constraints not registered, or no device functor for this dimension: generic route
+            self._fid = None
         self._torch = (self._fid is None and sfield is not None and _is_torch_vectorized(sfield)
                        and all(_is_torch_vectorized(g) for g in (self.g_cons or ())))
         # state

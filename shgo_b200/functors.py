@@ -125,6 +125,28 @@ def functor_id(func):
     return None
 
 
+MAX_FUSED_DIM = 32      # kMaxDim of csrc/common.cuh
+
+
+def supports(fid, gid, d):
+    """Does the device functor `fid` with constraint set `gid` exist for dimension d?  Mirrors the
+    dim_ok() rules of csrc/functors.cuh; DeviceComplex sends anything else down the generic route
+    (the user's own callable, evaluated per vertex like the reference does)."""
+    if fid is None or gid is None or not 1 <= d <= MAX_FUSED_DIM:
+        return False
+    if fid == F_ROSENBROCK:
+        return d >= 2 and gid == G_NONE
+    if fid in (F_RASTRIGIN, F_ACKLEY, F_STYBLINSKI_TANG):
+        return gid == G_NONE
+    if fid == F_EGGHOLDER:
+        return d == 2 and gid == G_NONE
+    if fid == F_CATTLE_FEED:
+        return d == 4 and gid in (G_NONE, G_CATTLE_FEED)
+    if fid == F_SPHERE:
+        return gid == G_NONE or (gid == G_SUM_LE_6 and d < 8)
+    return False
+
+
 def constraint_set_id(g_cons, g_args=None):
     """Device constraint-set id of a tuple of `ineq` callables: G_NONE for no constraints, the id
     when the tuple is exactly one registered set in order, else None."""

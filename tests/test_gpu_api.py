@@ -130,33 +130,6 @@ def test_infeasible_and_flat_problems(sb):
     assert not res.success and res.nfev == 0
 
 
-@pytest.mark.parametrize("bounds", [[(-3.3, 7.1)] * 3, [(0.1, 0.7)] * 2, [(0.3, 1.9), (-3.3, 7.1)]])
-def test_lattice_artefact_bounds_follow_the_reference(sb, bounds):
-    """Bounds whose fp64 midpoints depend on the split direction: the reference builds near-duplicate
-    vertices there, the closed-form lattice does not apply, and the complex replays the reference's
-    own generator instead -- same vertex count, nfev and minima as the reference."""
-    from shgo_b200 import functors as F
-    kw = dict(n=None, iters=3, sampling_method="simplicial")
-    ref = _reference_run(F.sphere, bounds, **kw)
-    res = sb.shgo(F.sphere, bounds, **kw)
-    assert res.nfev == ref.nfev and res.nit == ref.nit and res.success == ref.success
-    np.testing.assert_allclose(np.sort(res.funl), np.sort(ref.funl), rtol=1e-9, atol=1e-12)
-    from shgo_b200 import api
-    s = sb.SHGO(F.sphere, bounds, **kw)
-    try:
-        s.iterate_complex()
-        s.iterate_complex()
-        s.iterate_complex()
-    finally:
-        api.uninstall()
-    m = api.driver_module()
-    r = m.SHGO(F.sphere, bounds, **kw)
-    r.iterate_complex()
-    r.iterate_complex()
-    r.iterate_complex()
-    assert s.HC.mode == "hostgraph" and s.HC.V.size() == r.HC.V.size() and s.HC.V.nfev == r.HC.V.nfev
-
-
 @pytest.mark.parametrize("kw", [dict(n=None, iters=3), dict(n=30, iters=3), dict(n=70, iters=2)])
 def test_local_bounds_through_the_driver_seam(sb, kw):
     """SHGO.construct_lcb_simplicial served by the device kernels: identical

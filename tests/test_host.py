@@ -174,3 +174,26 @@ def test_lattice_insertion_key_against_the_reference_cache_order(name):
         assert np.array_equal(first, [born[tuple(c)] for c in coords]), (name, gen)
         g0 = first == 0
         assert np.array_equal(np.argsort(sec[g0], kind="stable"), np.arange(int(g0.sum()))), (name, gen)
+
+
+def test_functor_support_table_mirrors_the_device_dispatch():
+    """functors.supports() must agree with the SHGO_CASE table of csrc/eval.cu and the dim_ok() rules
+    of csrc/functors.cuh: anything else has to take the generic route instead of failing on the device."""
+    from shgo_b200 import functors as F
+    src = open(os.path.join(ROOT, "shgo_b200", "csrc", "eval.cu")).read()
+    pairs = set(re.findall(r"SHGO_CASE\(SHGO_B200_F_(\w+), SHGO_B200_G_(\w+),", src))
+    names_f = {"ROSENBROCK": F.F_ROSENBROCK, "RASTRIGIN": F.F_RASTRIGIN, "ACKLEY": F.F_ACKLEY,
+               "STYBLINSKI_TANG": F.F_STYBLINSKI_TANG, "EGGHOLDER": F.F_EGGHOLDER,
+               "CATTLE_FEED": F.F_CATTLE_FEED, "SPHERE": F.F_SPHERE}
+    names_g = {"NONE": F.G_NONE, "CATTLE_FEED": F.G_CATTLE_FEED, "SUM_LE_6": F.G_SUM_LE_6}
+    table = {(names_f[a], names_g[b]) for a, b in pairs}
+    for fid in names_f.values():
+        for gid in names_g.values():
+            any_dim = any(F.supports(fid, gid, d) for d in range(1, 33))
+            assert any_dim == ((fid, gid) in table), (fid, gid)
+    assert not F.supports(F.F_ROSENBROCK, F.G_NONE, 1) and F.supports(F.F_ROSENBROCK, F.G_NONE, 2)
+    assert F.supports(F.F_EGGHOLDER, F.G_NONE, 2) and not F.supports(F.F_EGGHOLDER, F.G_NONE, 3)
+    assert F.supports(F.F_CATTLE_FEED, F.G_CATTLE_FEED, 4) and not F.supports(F.F_CATTLE_FEED, F.G_NONE, 5)
+    assert F.supports(F.F_SPHERE, F.G_SUM_LE_6, 7) and not F.supports(F.F_SPHERE, F.G_SUM_LE_6, 8)
+    assert not F.supports(F.F_RASTRIGIN, F.G_NONE, 33) and not F.supports(None, F.G_NONE, 3)
+    assert not F.supports(F.F_RASTRIGIN, None, 3)

@@ -79,6 +79,9 @@ def test_random_problems_match_the_driver_with_its_python_complex(monkeypatch, s
             c = float(rng.uniform(-2, 6))
             cons = ({"type": "ineq", "fun": lambda x, *a, c=c: c - x[0] - x[1]},
                     {"type": "eq", "fun": lambda x, *a: x[0] - x[1]})
+        elif r < 0.45 and fn is not _pyargs:
+            # a REGISTERED constraint set: fused with Sphere, generic route with every other objective
+            cons = ({"type": "ineq", "fun": F.sum_le_6},)
         ref = m.shgo(fn, bounds, constraints=cons, **kw)
         res = shgo_b200.shgo(fn, bounds, constraints=cons, **kw)
         what = (seed, trial, getattr(fn, "__name__", "?"), bounds, kw, cons is not None)
