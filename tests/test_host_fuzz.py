@@ -89,3 +89,57 @@ def test_random_problems_match_the_driver_with_its_python_complex(monkeypatch, s
         a, b = np.sort(np.atleast_1d(getattr(res, "funl", []))), np.sort(np.atleast_1d(getattr(ref, "funl", [])))
         assert len(a) == len(b), what
         np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-8, err_msg=str(what))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_problems_match_iteration_by_iteration(monkeypatch, seed):
+    """The same differential idea at the level of the complex: after every `iterate()` the device
+    complex and the driver's Python complex agree on vertex count, nfev, the pool (as a set; in its
+    exact order wherever the complex is a mesh or a partial generation), the lowest vertex, the
+    number of local minima found so far and the neighbour sets of every pool vertex."""
+    fake_hotpath.install(monkeypatch)
+    import shgo_b200
+    from shgo_b200 import api, functors as F
+    m = api.driver_module()
+    funs = [F.rastrigin, F.ackley, F.styblinski_tang, F.sphere, _pyfun]
+    rng = np.random.default_rng(2000 + seed)
+    for trial in range(15):
+        d = int(rng.integers(1, 4))
+        fn = funs[int(rng.integers(0, len(funs)))]
+        lo = np.round(rng.uniform(-6, 0, d), 1)
+        hi = lo + np.round(rng.uniform(0.5, 8, d), 1) + 0.5
+        bounds = list(zip(lo.tolist(), hi.tolist()))
+        method = ["simplicial", "sobol", "halton"][int(rng.integers(0, 3))]
+        kw = dict(sampling_method=method, iters=3)
+        if method == "simplicial":
+            kw["n"] = [None, int(rng.integers(1, 40)), 2 ** d + 1][int(rng.integers(0, 3))]
+        else:
+            kw["n"] = int(rng.integers(4, 64))
+        cons = None
+        if rng.random() < 0.3 and d >= 2:
+            c = float(rng.uniform(-2, 6))
+            cons = ({"type": "ineq", "fun": lambda x, c=c: c - x[0] - x[1]},)
+        what = (seed, trial, getattr(fn, "__name__", "?"), bounds, kw, cons is not None)
+        r = m.SHGO(fn, bounds, constraints=cons, **kw)
+        s = shgo_b200.SHGO(fn, bounds, constraints=cons, **kw)
+        try:
+            for it in range(3):
+                r.iterate()
+                s.iterate()
+                assert (r.HC.V.size(), r.HC.V.nfev) == (s.HC.V.size(), s.HC.V.nfev), (what, it)
+                rx = [tuple(np.round(x, 12)) for x in np.atleast_2d(r.X_min)] if len(r.X_min) else []
+                sx = [tuple(np.round(x, 12)) for x in np.atleast_2d(s.X_min)] if len(s.X_min) else []
+                assert sorted(rx) == sorted(sx), (what, it)
+                if s.HC.mode != "lattice":
+                    assert rx == sx, (what, it, s.HC.mode)
+                r.find_lowest_vertex()
+                s.find_lowest_vertex()
+                assert (r.f_lowest is None) == (s.f_lowest is None), (what, it)
+                if r.f_lowest is not None:
+                    assert np.isclose(r.f_lowest, s.f_lowest, rtol=1e-9, atol=1e-12), (what, it)
+                assert len(r.LMC.xl_maps) == len(s.LMC.xl_maps), (what, it)
+                for v in getattr(s, "minimizer_pool", []):
+                    rv = r.HC.V.cache[v.x]
+                    assert {w.x for w in rv.nn if w is not rv} == {w.x for w in v.nn if w is not v}, (what, it, v.x)
+        finally:
+            api.uninstall()
