@@ -197,3 +197,19 @@ def test_functor_support_table_mirrors_the_device_dispatch():
     assert F.supports(F.F_SPHERE, F.G_SUM_LE_6, 7) and not F.supports(F.F_SPHERE, F.G_SUM_LE_6, 8)
     assert not F.supports(F.F_RASTRIGIN, F.G_NONE, 33) and not F.supports(None, F.G_NONE, 3)
     assert not F.supports(F.F_RASTRIGIN, None, 3)
+
+
+def test_cpu_stand_in_has_the_signatures_of_the_real_hot_path():
+    """tests/fake_hotpath.py replaces shgo_b200.hotpath in the CPU tests of the host logic: a call the
+    stand-in accepts must be one the real function accepts (same parameter names, same order)."""
+    import inspect
+    import fake_hotpath
+    from shgo_b200 import hotpath
+    src = inspect.getsource(fake_hotpath.install)
+    names = re.findall(r'"(\w+)"', src[src.index("for name in"):src.index("monkeypatch.setattr(hp, name")])
+    assert len(names) >= 18
+    for n in names:
+        real, fake = getattr(hotpath, n), getattr(fake_hotpath, n)
+        if inspect.isclass(real):
+            real, fake = real.__init__, fake.__init__
+        assert list(inspect.signature(real).parameters) == list(inspect.signature(fake).parameters), n
