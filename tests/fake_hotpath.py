@@ -186,12 +186,39 @@ def lattice_local_bounds(d, gen, tab, pool, bounds):
     return torch.from_numpy(lo), torch.from_numpy(hi)
 
 
+# what the C ABI silently assumes of every tensor it is handed: contiguous memory of the exact type
+_DTYPES = {"f": torch.float64, "f_all": torch.float64, "f_own": torch.float64, "g": torch.float64,
+           "x_soa": torch.float64, "tab": torch.float64, "feasible": torch.uint8, "is_min": torch.uint8,
+           "flags": torch.uint8, "present": torch.uint8, "row_ptr": torch.int64, "row_ptr_local": torch.int64,
+           "col": torch.int32, "col_local": torch.int32, "simplices": torch.int32, "pool": None, "nfev": torch.int64}
+
+
+def _strict(fn):
+    import functools
+    import inspect
+    sig = inspect.signature(fn)
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        bound = sig.bind(*args, **kwargs)
+        for name, val in bound.arguments.items():
+            if isinstance(val, torch.Tensor):
+                assert val.is_contiguous(), "%s(%s): non-contiguous tensor handed to the hot path" % (fn.__name__, name)
+                want = _DTYPES.get(name)
+                if want is not None:
+                    assert val.dtype == want, "%s(%s): dtype %s, the C ABI reads %s" % (fn.__name__, name, val.dtype, want)
+        return fn(*args, **kwargs)
+    wrapper.__signature__ = sig
+    return wrapper
+
+
 def install(monkeypatch):
     """Patch shgo_b200.hotpath in place (functions are looked up as attributes at call time)."""
     from shgo_b200 import hotpath as hp
     for name in ("SobolTables", "sobol_points", "eval_sobol", "eval_points", "mask_infeasible",
                  "csr_from_simplices", "first_seen", "star_csr", "star_csr_shard", "PoolWorkspace", "compact_pool", "argmin", "lattice_eval",
                  "lattice_coords", "lattice_star", "local_bounds_csr", "lattice_local_bounds", "lattice_eval_push"):
-        monkeypatch.setattr(hp, name, globals()[name])
+        obj = globals()[name]
+        monkeypatch.setattr(hp, name, obj if isinstance(obj, type) else _strict(obj))
     monkeypatch.setattr(hp, "_require_cuda", lambda: None)
     monkeypatch.setattr(hp, "_dev", lambda device=None: CPU)
