@@ -134,11 +134,17 @@ def _device_sampler(n, bounds, sampling_method):
     return n, sampler, sampler
 
 
+# Set to False to keep options['local_iter'] calls on the closed-form lattice (fast; the first local
+# search may then start from a different pool vertex of the same generation than the reference's).
+EXACT_CACHE_ORDER = True
+
+
 def _needs_cache_order(options, sampling_method):
     """options['local_iter'] starts its local searches from X_min[0], the pool vertex the reference's
     cache created first (_shgo.py:1177); on the simplicial complex that order has a closed form only
     across generations, so such a call gets its graph from the reference's generator."""
-    return bool(options and options.get("local_iter")) and sampling_method == "simplicial"
+    return (EXACT_CACHE_ORDER and bool(options and options.get("local_iter"))
+            and sampling_method == "simplicial")
 
 
 def SHGO(func, bounds, args=(), constraints=None, n=None, iters=None, callback=None,
