@@ -82,7 +82,7 @@ def _lattice_worker(rank, world, init_file, out_dir, d, gen):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,d,gen", [(2, 5, 2), (4, 2, 6), (2, 3, 0)])
+@pytest.mark.parametrize("world,d,gen", [(2, 5, 2), (4, 2, 6), (2, 3, 0), (3, 4, 3)])
 def test_sharded_lattice_generation_matches_single_rank(world, d, gen):
     """SURVEY.md 8(e), lattice path: granule-cyclic ownership (4096 ids per granule: the cases
     span 2, 3 and 1 granules); the union of the ranks' pools equals the oracle's pool of the whole
