@@ -15,6 +15,8 @@ driver's official custom-sampling seam (``sampling_method`` callable f(n, d), _s
 """
 import contextlib
 import importlib
+import threading
+import types
 
 import numpy as np
 
@@ -37,59 +39,73 @@ def driver_module(name=None):
     raise ImportError("no SHGO driver found (tried %s): %s" % (", ".join(_DRIVERS), last))
 
 
+_LOCK = threading.RLock()     # install / uninstall edit module globals of the driver
+
+
+def _device_lcb(saved):
+    """construct_lcb_simplicial (_shgo.py:1246-1270) served from the device when the complex is a
+    DeviceComplex: no neighbour objects are created; any other complex gets the driver's own."""
+    def construct_lcb_simplicial(self, v_min):
+        if isinstance(self.HC, _cx.DeviceComplex):
+            cbounds = self.HC.local_bounds(v_min, self.bounds)
+            if self.disp:
+                import logging
+                logging.info(f'cbounds found for v_min.x_a = {v_min.x_a}')
+                logging.info(f'cbounds = {cbounds}')
+            return cbounds
+        return saved(self, v_min)
+
+    construct_lcb_simplicial.__doc__ = saved.__doc__
+    return construct_lcb_simplicial
+
+
 def install(driver=None):
     """Rebind ``Complex`` in the driver module to DeviceComplex (what INTEGRATION.md asks a
-    reference maintainer to do in one line).  Returns the driver module."""
-    m = driver_module(driver)
-    cm = importlib.import_module(_COMPLEX_MODULES[m.__name__])
-    _cx._ORIGINAL_COMPLEX.setdefault(cm.__name__, cm.Complex)
-    if m.Complex is not _cx.DeviceComplex:
-        m._shgo_b200_saved_complex = m.Complex
-        m.Complex = _cx.DeviceComplex
-    _cx.DeviceComplex.scipy_constraint_rule = m.__name__.startswith("scipy.")
-    # local bounds of a pool vertex (construct_lcb_simplicial, _shgo.py:1246-1270) come from the
-    # device when the complex is a DeviceComplex: no neighbour objects are created
-    if not hasattr(m.SHGO, "_shgo_b200_saved_lcb"):
-        saved = m.SHGO.construct_lcb_simplicial
-
-        def construct_lcb_simplicial(self, v_min):
-            if isinstance(self.HC, _cx.DeviceComplex):
-                cbounds = self.HC.local_bounds(v_min, self.bounds)
-                if self.disp:
-                    import logging
-                    logging.info(f'cbounds found for v_min.x_a = {v_min.x_a}')
-                    logging.info(f'cbounds = {cbounds}')
-                return cbounds
-            return saved(self, v_min)
-
-        construct_lcb_simplicial.__doc__ = saved.__doc__
-        m.SHGO._shgo_b200_saved_lcb = saved
-        m.SHGO.construct_lcb_simplicial = construct_lcb_simplicial
-    return m
+    reference maintainer to do in one line).  Returns the driver module.  This is a process-wide
+    patch of the driver module: every later ``shgo()`` of that driver runs on the device until
+    :func:`uninstall`.  ``shgo_b200.shgo`` / ``shgo_b200.SHGO`` scope it to their own call."""
+    with _LOCK:
+        m = driver_module(driver)
+        cm = importlib.import_module(_COMPLEX_MODULES[m.__name__])
+        _cx._ORIGINAL_COMPLEX.setdefault(cm.__name__, cm.Complex)
+        if m.Complex is not _cx.DeviceComplex:
+            m._shgo_b200_saved_complex = m.Complex
+            m.Complex = _cx.DeviceComplex
+        _cx.DeviceComplex.scipy_constraint_rule = m.__name__.startswith("scipy.")
+        if not hasattr(m.SHGO, "_shgo_b200_saved_lcb"):
+            saved = m.SHGO.construct_lcb_simplicial
+            m.SHGO._shgo_b200_saved_lcb = saved
+            m.SHGO.construct_lcb_simplicial = _device_lcb(saved)
+        return m
 
 
 def uninstall(driver=None):
-    m = driver_module(driver)
-    saved = getattr(m, "_shgo_b200_saved_complex", None)
-    if saved is not None:
-        m.Complex = saved
-        del m._shgo_b200_saved_complex
-    if hasattr(m.SHGO, "_shgo_b200_saved_lcb"):
-        m.SHGO.construct_lcb_simplicial = m.SHGO._shgo_b200_saved_lcb
-        del m.SHGO._shgo_b200_saved_lcb
-    return m
+    with _LOCK:
+        m = driver_module(driver)
+        saved = getattr(m, "_shgo_b200_saved_complex", None)
+        if saved is not None:
+            m.Complex = saved
+            del m._shgo_b200_saved_complex
+        if hasattr(m.SHGO, "_shgo_b200_saved_lcb"):
+            m.SHGO.construct_lcb_simplicial = m.SHGO._shgo_b200_saved_lcb
+            del m.SHGO._shgo_b200_saved_lcb
+        _cx.DeviceComplex.scipy_constraint_rule = False
+        return m
 
 
 @contextlib.contextmanager
 def _installed(driver=None):
-    m = driver_module(driver)
-    already = m.Complex is _cx.DeviceComplex
-    install(driver)
-    try:
-        yield m
-    finally:
-        if not already:
-            uninstall(driver)
+    """install() for the duration of the block only (held under a lock: the patch is a module
+    global of the driver, two threads must not interleave install / uninstall)."""
+    with _LOCK:
+        m = driver_module(driver)
+        already = m.Complex is _cx.DeviceComplex
+        install(driver)
+        try:
+            yield m
+        finally:
+            if not already:
+                uninstall(driver)
 
 
 class DeviceSobolSampler:
@@ -151,16 +167,23 @@ def SHGO(func, bounds, args=(), constraints=None, n=None, iters=None, callback=N
          minimizer_kwargs=None, options=None, sampling_method="simplicial", workers=1, driver=None):
     """The driver's SHGO object (same constructor as shgo/_shgo.py:491) with ``HC`` on the device.
     Use it like the reference's: ``s.iterate_all()``, ``s.iterate()``, ``s.res`` ..."""
-    m = install(driver)
-    n, sampling_method, sampler = _device_sampler(n, bounds, sampling_method)
-    # picked up by the DeviceComplex the driver constructs
-    _cx.set_pending_sampler(sampler, _needs_cache_order(options, sampling_method))
-    try:
-        return m.SHGO(func, bounds, args=args, constraints=constraints, n=n, iters=iters, callback=callback,
-                      minimizer_kwargs=minimizer_kwargs, options=options, sampling_method=sampling_method,
-                      workers=workers)
-    finally:
-        _cx.set_pending_sampler(None)
+    # The patch of the driver module lasts for the construction only (HC is built inside
+    # SHGO.__init__, _shgo.py:680-684): a later plain `scipy.optimize.shgo` / reference `shgo` call
+    # in the same process is not rerouted.  What the object needs afterwards is bound to it.
+    with _installed(driver) as m:
+        n, sampling_method, sampler = _device_sampler(n, bounds, sampling_method)
+        # picked up by the DeviceComplex the driver constructs
+        _cx.set_pending_sampler(sampler, _needs_cache_order(options, sampling_method))
+        try:
+            obj = m.SHGO(func, bounds, args=args, constraints=constraints, n=n, iters=iters, callback=callback,
+                         minimizer_kwargs=minimizer_kwargs, options=options, sampling_method=sampling_method,
+                         workers=workers)
+        finally:
+            _cx.set_pending_sampler(None)
+        saved = getattr(m.SHGO, "_shgo_b200_saved_lcb", m.SHGO.construct_lcb_simplicial)
+    obj.construct_lcb_simplicial = types.MethodType(_device_lcb(saved), obj)
+    obj.HC.scipy_constraint_rule = m.__name__.startswith("scipy.")
+    return obj
 
 
 def shgo(func, bounds, args=(), constraints=None, n=100, iters=1, callback=None,

@@ -53,6 +53,7 @@ from . import lattice as lat
 
 
 _PENDING = threading.local()
+LATTICE_MAX_DIM = 12     # closed-form star / local-bounds kernels (csrc/lattice.cu, bounds.cu); above: generator replay
 
 
 def set_pending_sampler(sampler, exact_cache_order=False):
@@ -409,6 +410,11 @@ class DeviceComplex:
         split direction make it create near-duplicate vertices, SURVEY.md section 7 hard part 6):
         the caller then replays the reference's own generator (hostgraph) so that the result stays
         identical to the reference's, duplicates included."""
+        # limits of the closed-form kernels (lattice.cu / bounds.cu: d <= 12, < 2^32 vertices): beyond
+        # them the reference's generator is replayed like for artefact bounds -- the reference still
+        # works there (slowly), so must this
+        if self.dim > LATTICE_MAX_DIM or lat.counts(self.dim, gen)[0] >= 2 ** 32:
+            return False
         try:
             tab = lat.coordinate_tables(self.bounds, gen)
         except lat.LatticeArtefactError:
@@ -419,8 +425,6 @@ class DeviceComplex:
         self._lat_gen = gen
         self.gen = gen
         self._n, self._ngrid = lat.counts(self.dim, gen)
-        if self._n >= 2 ** 32:
-            raise MemoryError("generation %d of a %d-D lattice has %d vertices" % (gen, self.dim, self._n))
         self._dirty = True
         return True
 
@@ -754,12 +758,13 @@ class DeviceComplex:
 
     def _sampler_tables_if_points_are_sobol(self, pts):
         """The fused generate->evaluate kernel applies when the mesh's points are exactly Sobol
-        indices [0, n) of the registered device sampler (checked on a few rows)."""
+        indices [0, n) of the registered device sampler: every row is compared (cheap next to the
+        qhull run that produced the mesh), so a caller that edited an interior row gets the uploaded
+        points evaluated, not the regenerated ones."""
         s = self._sampler
         if s is None or s.total != pts.shape[0] or s.host is None:
             return None
-        probe = np.unique(np.clip(np.array([0, 1, pts.shape[0] // 2, pts.shape[0] - 1]), 0, pts.shape[0] - 1))
-        if not np.array_equal(pts[probe], s.host[probe]):
+        if s.host.shape != pts.shape or not np.array_equal(pts, s.host):
             return None
         return s.tab
 

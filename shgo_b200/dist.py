@@ -131,14 +131,18 @@ class ShardedSobolIteration:
             ws = _lib.lib().shgo_b200_star_remote_workspace(self.rows, self.rows)
             self._remote_tmp = torch.empty(ws, dtype=torch.uint8, device=dev)
             # phase 1 lists its candidates here, phase 2 consumes the list (no compaction pass)
-            self._cand_ws = torch.empty(_lib.lib().shgo_b200_star_local_workspace(self.rows),
-                                        dtype=torch.uint8, device=dev)
+            # one list per chunk: phase 2 of chunk c reads its list on the `_remote` stream while
+            # phase 1 of chunk c+1 is already writing the next one on the main stream
+            self.chunks = max(1, int(chunks))
+            per = self.rows // self.chunks
+            self._chunk_rows = [per if c < self.chunks - 1 else self.rows - c * per for c in range(self.chunks)]
+            self._cand_ws = [torch.empty(_lib.lib().shgo_b200_star_local_workspace(nr), dtype=torch.uint8,
+                                         device=dev) for nr in self._chunk_rows]
             self._comm = torch.cuda.Stream(device=dev)
             self._remote = torch.cuda.Stream(device=dev)
             # chunks > 1 pipelines phase 2 of one chunk under phase 1 of the next on a second stream;
             # measured on B200 it does not pay (the persistent phase-1 kernel leaves no room for the
             # phase-2 CTAs to co-run), so the default is a single chunk
-            self.chunks = int(chunks)
             self._nfev_parts = torch.zeros(self.chunks, dtype=torch.int64, device=dev)
         else:
             self.f_all = torch.empty(n if self.world > 1 else self.rows, dtype=torch.float64, device=dev)
@@ -173,19 +177,17 @@ class ShardedSobolIteration:
             self._barrier_async()
             main = torch.cuda.current_stream()
             self._remote.wait_stream(self._comm)
-            C = self.chunks
-            per = self.rows // C
-            for c in range(C):
-                r0 = self.row0 + c * per
-                nr = per if c < C - 1 else self.rows - c * per
+            r0 = self.row0
+            for c, nr in enumerate(self._chunk_rows):
                 hp.star_csr_local(self.row_ptr, self.col, self.row0, self.f_my, self.feas, self.is_min,
-                                  self._nfev_parts[c:c + 1], self.off0, r0, nr, self._cand_ws, self.remote_at_ends)
+                                  self._nfev_parts[c:c + 1], self.off0, r0, nr, self._cand_ws[c], self.remote_at_ends)
                 self._remote.wait_stream(main)
                 with torch.cuda.stream(self._remote):
                     hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table,
                                        self.peer.own_ptr, self.world, self.rows, self.rank, self.is_min,
                                        self._remote_tmp, self.off0, r0, nr, self.remote_at_ends,
-                                       self._cand_ws)
+                                       self._cand_ws[c])
+                r0 += nr
             main.wait_stream(self._remote)
             torch.sum(self._nfev_parts, 0, keepdim=True, out=self.nfev)
         else:

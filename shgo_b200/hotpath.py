@@ -57,6 +57,21 @@ class SobolTables:
 MAX_FUSED_DIM = 32      # kMaxDim of the kernels (tables live in shared memory)
 
 
+def soa_ld(x_soa):
+    """Leading dimension (elements between consecutive coordinate rows) of a (d, n) coordinate-major
+    tensor, as the C ABI wants it (`ld >= n`, include/shgo_b200.h).  torch reports an arbitrary
+    stride for a dimension of size 1 (`(n, 1).t().contiguous()` keeps stride(0) == 1), so a single
+    row, or an empty tensor, gets ld = max(n, 1): the value is never used to step between rows."""
+    assert x_soa.dim() == 2 and (x_soa.shape[1] <= 1 or x_soa.stride(1) == 1), "rows must be unit-stride"
+    d, n = x_soa.shape
+    if d <= 1 or n == 0:
+        return max(n, 1)
+    ld = x_soa.stride(0)
+    if ld < n:
+        raise ValueError("coordinate rows overlap: stride(0) = %d < n = %d" % (ld, n))
+    return ld
+
+
 def sobol_points(tab, k0, n, layout="soa", out=None):
     """Points k0..k0+n-1 scaled to the bounds, bit-identical to the reference's `self.C`.
 
@@ -76,7 +91,7 @@ def sobol_points(tab, k0, n, layout="soa", out=None):
     if layout == "soa":
         x = out if out is not None else torch.empty((d, n), dtype=torch.float64, device=dev)
         _lib.call("shgo_b200_sobol_fill", _ptr(tab.sv), d, k0, n, _ptr(tab.lb), _ptr(tab.ub), _ptr(x),
-                  x.stride(0) if n else max(n, 1), 0, _stream())
+                  soa_ld(x), 0, _stream())
     else:
         x = out if out is not None else torch.empty((n, d), dtype=torch.float64, device=dev)
         _lib.call("shgo_b200_sobol_fill", _ptr(tab.sv), d, k0, n, _ptr(tab.lb), _ptr(tab.ub), _ptr(x),
@@ -98,13 +113,13 @@ def eval_sobol(functor, gset, tab, k0, n, f=None, feasible=None, want_feasible=T
 
 def eval_points(functor, gset, x_soa, f=None, feasible=None):
     """Evaluate a registered functor on caller-supplied points, x_soa = (d, n) float64."""
-    assert x_soa.dtype == torch.float64 and x_soa.dim() == 2 and x_soa.stride(1) == 1
+    assert x_soa.dtype == torch.float64 and x_soa.dim() == 2
     d, n = x_soa.shape
     if f is None:
         f = torch.empty(n, dtype=torch.float64, device=x_soa.device)
     if feasible is None:
         feasible = torch.empty(n, dtype=torch.uint8, device=x_soa.device)
-    _lib.call("shgo_b200_eval_points", functor, gset, d, n, _ptr(x_soa), x_soa.stride(0) if n else 1,
+    _lib.call("shgo_b200_eval_points", functor, gset, d, n, _ptr(x_soa), soa_ld(x_soa),
               _ptr(f), _ptr(feasible), _stream())
     return f, feasible
 
@@ -330,7 +345,8 @@ def _bounds_vectors(bounds, d, dev):
 def local_bounds_csr(row_ptr, col, x_soa, pool, bounds):
     """construct_lcb_simplicial (_shgo.py:1246-1270) of the vertices `pool` of an explicit graph;
     x_soa is (d, ld) coordinate-major.  -> lo, hi of shape (m, d)."""
-    d, ld = x_soa.shape
+    d = x_soa.shape[0]
+    ld = soa_ld(x_soa)
     dev = x_soa.device
     pool = pool.to(device=dev, dtype=torch.int64).contiguous()
     m = pool.numel()

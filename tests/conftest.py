@@ -62,3 +62,21 @@ def gset_of(g):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+def pytest_terminal_summary(terminalreporter):
+    """worst observed f error per functor (tests/tolerance.py), also left in gpurun_out/ on a GPU box"""
+    import tolerance
+    if not tolerance.WORST:
+        return
+    text = tolerance.report()
+    terminalreporter.write_line(text)
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        try:
+            import torch
+            tag = "gpu" if torch.cuda.is_available() else "cpu"
+            with open(os.path.join(out, "f_tolerance_%s.txt" % tag), "w") as fh:
+                fh.write(text + "\n")
+        except Exception:
+            pass

@@ -2,8 +2,8 @@
 
 Every call goes through the C ABI (shgo_b200.hotpath is a ctypes shim over libshgo_b200.so).
 Bars: Sobol points, adjacency, feasibility and pool index sets bit-exact; f bit-exact for the
-polynomial / FMA-chain functors and within 1e-12 (relative to max(|f|, 1)) for the ones that go
-through cos/sin/exp.
+polynomial / FMA-chain functors and within 1e-12 RELATIVE for the ones that go through cos/sin/exp,
+with the documented absolute floor of tests/tolerance.py (4 ulp of the largest term of the sum).
 """
 import numpy as np
 import pytest
@@ -16,8 +16,9 @@ pytestmark = pytest.mark.gpu
 
 from oracle import oracle as orc  # noqa: E402
 
+import tolerance  # noqa: E402
+
 DEVICE_BIT_EXACT = BIT_EXACT_F | {"styblinski_tang"}   # device == C oracle bit for bit
-RTOL = 1e-12
 
 
 @pytest.fixture(scope="module")
@@ -32,12 +33,9 @@ def _ids(functor, gset):
     return orc.FUNCTOR_IDS[functor], orc.GSET_IDS[gset]
 
 
-def _close(a, b):
-    fin = np.isfinite(b)
-    assert np.array_equal(np.isinf(a), np.isinf(b))
-    if fin.any():
-        scale = np.maximum(np.abs(b[fin]), 1.0)
-        assert np.max(np.abs(a[fin] - b[fin]) / scale) < RTOL
+def _close(a, b, functor, x):
+    """north_star's bar: 1e-12 relative (+ the explicit floor, tests/tolerance.py); x = (n, d) points"""
+    tolerance.assert_close(a, b, functor, x)
 
 
 # ------------------------------------------------------------------------------------------
@@ -106,6 +104,9 @@ EVAL_CASES = [
     ("eggholder", None, [(-512, 512)] * 2),
     ("cattle_feed", None, [(0, 1.0)] * 4), ("cattle_feed", "cattle_feed", [(0, 1.0)] * 4),
     ("sphere", None, [(-1, 6)] * 4), ("sphere", "sum_le_6", [(-1, 6)] * 2),
+    # one axis: torch gives a (1, n) tensor an arbitrary stride(0) (round-1 failure `ld < n`)
+    ("sphere", None, [(-1, 6)]), ("rastrigin", None, [(-2.1, 4.4)]), ("styblinski_tang", None, [(-2.0, 6.2)]),
+    ("ackley", None, [(-3.0, 5.0)]),
 ]
 
 
@@ -124,7 +125,7 @@ def test_eval_sobol_vs_oracle(hp, functor, gset, bounds):
         if functor in DEVICE_BIT_EXACT:
             assert np.array_equal(f, fo)
         else:
-            _close(f, fo)
+            _close(f, fo, functor, orc.sobol_points(sv, k0, n, b[:, 0], b[:, 1]))
         # same evaluation on materialised points
         x = hp.sobol_points(tab, k0, n, "soa")
         f2, feas2 = hp.eval_points(fid, gid, x)
@@ -145,7 +146,54 @@ def test_eval_matches_numpy_callables(hp):
         if fn in (F.rosenbrock, F.cattle_feed):
             assert np.array_equal(f, ref)
         else:
-            _close(f, ref)
+            _close(f, ref, fn.__name__, x)
+
+
+@pytest.mark.parametrize("functor,d,lo,hi", [
+    ("rastrigin", 1, -2.1, 4.4), ("styblinski_tang", 1, -2.0, 6.2), ("sphere", 1, -1.0, 6.0),
+    ("ackley", 1, -3.0, 5.0), ("rastrigin", 6, -5.12, 5.12), ("ackley", 10, -32.768, 32.768),
+    ("eggholder", 2, -512.0, 512.0), ("rosenbrock", 5, 0.0, 2.0),
+])
+def test_eval_points_on_non_sobol_points(hp, functor, d, lo, hi):
+    """Halton / custom-sampler / second-iteration route: the host hands over an (n, d) array, the
+    complex uploads it as `torch.from_numpy(pts).cuda().t().contiguous()` (complex.py) -- for d = 1
+    that tensor has stride(0) == 1.  Every registered functor, odd n, also through a strided view."""
+    rng = np.random.default_rng(d * 7 + len(functor))
+    for n in (1, 94, 4097):
+        pts = rng.uniform(lo, hi, size=(n, d))
+        x = torch.from_numpy(pts).cuda().t().contiguous()
+        f, feas = hp.eval_points(orc.FUNCTOR_IDS[functor], 0, x)
+        fo, feo = orc.eval_points(functor, None, pts)
+        assert np.array_equal(feas.cpu().numpy(), feo)
+        if functor in DEVICE_BIT_EXACT:
+            assert np.array_equal(f.cpu().numpy(), fo)
+        else:
+            _close(f.cpu().numpy(), fo, functor, pts)
+        wide = torch.zeros((d, n + 13), dtype=torch.float64, device="cuda")     # ld > n
+        wide[:, :n] = x
+        f2, _ = hp.eval_points(orc.FUNCTOR_IDS[functor], 0, wide[:, :n])
+        assert torch.equal(f2, f)
+
+
+@pytest.mark.parametrize("functor,d,width", [("ackley", 10, 32.768), ("ackley", 3, 32.768), ("rastrigin", 6, 5.12),
+                                             ("rastrigin", 2, 5.12)])
+def test_transcendental_functors_near_their_minimum(hp, functor, d, width):
+    """Where an absolute tolerance would hide everything: f -> 0 at the origin (Ackley: the sum passes
+    through 20 + e; Rastrigin: through 10 d).  Points at distances 1e-1 ... 1e-9 from the minimiser,
+    the minimiser itself, and the neighbouring integer-lattice minima of Rastrigin."""
+    rng = np.random.default_rng(5)
+    pts = [np.zeros((1, d))]
+    for r in 10.0 ** -np.arange(1, 10):
+        pts.append(rng.standard_normal((400, d)) * r)
+    if functor == "rastrigin":
+        pts.append(np.round(rng.uniform(-4, 4, (400, d))) + rng.standard_normal((400, d)) * 1e-4)
+    pts = np.clip(np.concatenate(pts), -width, width)
+    x = torch.from_numpy(pts).cuda().t().contiguous()
+    f, _ = hp.eval_points(orc.FUNCTOR_IDS[functor], 0, x)
+    from shgo_b200 import functors as F
+    ref = np.array([getattr(F, functor)(p) for p in pts])         # the reference-side numpy callable
+    _close(f.cpu().numpy(), ref, functor, pts)
+    _close(f.cpu().numpy(), orc.eval_points(functor, None, pts)[0], functor, pts)
 
 
 def test_mask_infeasible(hp):
@@ -190,7 +238,7 @@ def test_golden_sobol_case(hp, name):
     if functor in BIT_EXACT_F:
         assert np.array_equal(fh[present], g["f"][present])
     else:
-        _close(fh[present], g["f"][present])
+        _close(fh[present], g["f"][present], functor, g["points"][present])
     # classify + pool + bookkeeping
     is_min = hp.star_csr(row_ptr, col, f)
     idx, cnt = hp.compact_pool(is_min)
@@ -302,7 +350,7 @@ def test_golden_simplicial_pools(hp, name):
         if functor in DEVICE_BIT_EXACT:
             assert np.array_equal(f.cpu().numpy(), fo)
         else:
-            _close(f.cpu().numpy(), fo)
+            _close(f.cpu().numpy(), fo, functor, x)
         is_min = hp.lattice_star(d, it, f).cpu().numpy()
         pool = {tuple(x[i]) for i in np.flatnonzero(is_min)} - started
         ref = {tuple(p) for p in g[f"pool_x_{it}"]}
@@ -320,7 +368,7 @@ def test_lattice_10d_generation1_vs_oracle(hp):
     f, _ = hp.lattice_eval(orc.FUNCTOR_IDS["ackley"], 0, d, gen, tab, 0, nv)
     fh = f.cpu().numpy()
     x = orc.lattice_coords(bounds, gen)
-    _close(fh, orc.eval_points("ackley", None, x)[0])
+    _close(fh, orc.eval_points("ackley", None, x)[0], "ackley", x)
     got = hp.lattice_star(d, gen, f).cpu().numpy()
     assert np.array_equal(got, orc.lattice_star(d, gen, fh))
     # sharded vertex ranges give the same flags
@@ -386,7 +434,7 @@ def test_host_buffer_iteration_matches_device_path(hp):
             _lib.call("shgo_b200_iterate_sobol_host", ctx, 1, 0, d, 0, n, sv.ctypes.data, lb.ctypes.data,
                       ub.ctypes.data, rp.ctypes.data, col.ctypes.data, pool.ctypes.data, n,
                       ctypes.byref(cnt), ctypes.byref(nfev), fout.ctypes.data)
-        _close(fout, fo)
+        _close(fout, fo, "rastrigin", orc.sobol_points(sv, 0, n, lb, ub))
         ref_pool = orc.compact_pool(orc.star_csr(rp, col, fout))
         assert np.array_equal(pool[: cnt.value], ref_pool)
         assert nfev.value == n
@@ -488,7 +536,7 @@ def test_baseline_configs_at_full_size(hp, functor, gset, bounds, log2n):
         if functor in DEVICE_BIT_EXACT:
             assert np.array_equal(f[k0:k0 + 8192].cpu().numpy(), fo)
         else:
-            _close(f[k0:k0 + 8192].cpu().numpy(), fo)
+            _close(f[k0:k0 + 8192].cpu().numpy(), fo, functor, orc.sobol_points(sv, k0, 8192, b[:, 0], b[:, 1]))
     assert bool(torch.isinf(f[feas == 0]).all()) and bool(torch.isfinite(f[feas == 1]).all())
     row_ptr, col = hp.hypercube_csr(n)
     nf = torch.zeros(1, dtype=torch.int64, device="cuda")

@@ -206,10 +206,43 @@ def test_cpu_stand_in_has_the_signatures_of_the_real_hot_path():
     import fake_hotpath
     from shgo_b200 import hotpath
     src = inspect.getsource(fake_hotpath.install)
-    names = re.findall(r'"(\w+)"', src[src.index("for name in"):src.index("monkeypatch.setattr(hp, name")])
+    names = re.findall(r'"(\w+)"', src[src.index("for name in"):src.index("obj = globals()[name]")])
     assert len(names) >= 18
     for n in names:
         real, fake = getattr(hotpath, n), getattr(fake_hotpath, n)
         if inspect.isclass(real):
             real, fake = real.__init__, fake.__init__
         assert list(inspect.signature(real).parameters) == list(inspect.signature(fake).parameters), n
+
+
+def test_soa_leading_dimension_of_single_row_tensors():
+    """torch reports stride 1 for the size-1 leading dimension of `(n, 1).t().contiguous()`; the C ABI
+    wants ld >= n (round-1 GPU failure: every 1-D problem on non-Sobol points raised `ld < n`)."""
+    import torch
+    from shgo_b200 import hotpath
+    x = torch.zeros(94, 1, dtype=torch.float64).t().contiguous()
+    assert x.stride(0) == 1 and hotpath.soa_ld(x) == 94
+    assert hotpath.soa_ld(torch.zeros(3, 7, dtype=torch.float64)) == 7
+    assert hotpath.soa_ld(torch.zeros(3, 16, dtype=torch.float64)[:, :5]) == 16
+    assert hotpath.soa_ld(torch.zeros(4, 0, dtype=torch.float64)) == 1
+    with pytest.raises(ValueError):
+        hotpath.soa_ld(torch.zeros(1, 8, dtype=torch.float64).expand(3, 8))
+
+
+def test_abi_contract_rejects_what_the_library_rejects():
+    """tests/abi_contract.py mirrors the SHGO_REQUIRE lines of csrc/*.cu: spot-check both directions."""
+    import abi_contract as A
+    with pytest.raises(A.AbiContractError, match="ld < n"):
+        A.check("shgo_b200_eval_points", 0, 0, 1, 94, 1000, 1, 2000, 3000, 0)
+    A.check("shgo_b200_eval_points", 0, 0, 1, 94, 1000, 94, 2000, 3000, 0)
+    with pytest.raises(A.AbiContractError):
+        A.check("shgo_b200_lattice_star_part", 13, 0, 1, 0, 10, 0, 1, 4096, 1, 1, 64, 0)
+    with pytest.raises(A.AbiContractError, match="no contract"):
+        A.check("shgo_b200_not_a_symbol")
+    # every compute symbol the product marshals has a contract
+    from shgo_b200 import _lib
+    skip = ("version", "last_error", "device_info", "workspace", "ipc_", "ctx_", "fp64_peak",
+            "iterate_sobol", "lattice_star")
+    for name in _lib.SIGNATURES:
+        if not any(k in name for k in skip) or name == "shgo_b200_lattice_star_part":
+            assert hasattr(A, name), name

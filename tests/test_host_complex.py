@@ -151,7 +151,7 @@ def test_local_bounds_through_the_driver_seam(sb, kw):
     s.iterate_complex()
     s.minimizers()
     m = api.driver_module()
-    reference_method = m.SHGO._shgo_b200_saved_lcb
+    reference_method = getattr(m.SHGO, "_shgo_b200_saved_lcb", m.SHGO.construct_lcb_simplicial)
     assert len(s.minimizer_pool) > 0
     boxes = [s.construct_lcb_simplicial(v) for v in s.minimizer_pool]
     assert len(s.HC.V._unlisted) == 0
@@ -222,3 +222,21 @@ def test_cases_found_by_the_differential_fuzz(sb, fname, bounds, kw):
     res = sb.shgo(fn, bounds, **kw)
     assert (res.success, res.nfev, res.nit, len(res.funl)) == (ref.success, ref.nfev, ref.nit, len(ref.funl))
     np.testing.assert_allclose(np.sort(res.funl), np.sort(ref.funl), rtol=1e-6, atol=1e-8)
+
+
+def test_shgo_object_does_not_leave_the_driver_patched(sb):
+    """shgo_b200.SHGO(...) binds the device complex for the construction only: a later plain driver
+    call in the same process gets the driver's own Python Complex again."""
+    from shgo_b200 import api, functors as F
+    from shgo_b200.complex import DeviceComplex
+    m = api.driver_module()
+    plain = m.Complex
+    assert plain is not DeviceComplex
+    s = sb.SHGO(F.sphere, [(-1.0, 2.0)] * 2, n=None, iters=1)
+    assert isinstance(s.HC, DeviceComplex)
+    assert m.Complex is plain and not hasattr(m.SHGO, "_shgo_b200_saved_lcb")
+    r = m.SHGO(F.sphere, [(-1.0, 2.0)] * 2, n=None, iters=1)
+    assert not isinstance(r.HC, DeviceComplex)
+    s.iterate_all()
+    r.iterate_all()
+    assert s.res.nfev == r.res.nfev and np.allclose(s.res.x, r.res.x)
