@@ -38,10 +38,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=28, help="log2 of the total number of points")
-    ap.add_argument("--e2e-log2n", type=int, default=26, help="log2 n of the host-buffer (e2e) leg")
-    ap.add_argument("--cpu-log2n", type=int, default=24, help="log2 n of the CPU baseline sample")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
+    ap.add_argument("--e2e-log2n", type=int, default=26,
+                    help="log2 n of the host-buffer (e2e) leg AND of the CPU arm's sample (same problem in both)")
+    ap.add_argument("--cpu-log2n", type=int, default=None, help="override the CPU sample size (default: --e2e-log2n)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "p2p", "allgather"],
                     help="how neighbour f values cross GPUs (N > 1)")
+    ap.add_argument("--chunks", type=int, default=1, help="p2p exchange: classify the shard in chunks (overlap)")
+    ap.add_argument("--phase1-warps", type=int, default=0, help="p2p + chunks: resident warps per SM of phase 1")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -164,12 +167,21 @@ def reference_arm(args):
         "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.log2n), "points": 1 << args.log2n,
-                   "sample_points_per_step": n},
+        "config": config_of(args),
+        "sample_points_per_step": n,
         "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def config_of(args):
+    """identical in both arms: the workload, and the size both the CPU arm and the e2e leg run"""
+    return {"workload": workload_name(args.log2n), "points": 1 << args.log2n,
+            "e2e_and_cpu_points": 1 << min(args.e2e_log2n, args.log2n),
+            "note": "value: device-resident 2^%d points; e2e (host buffers through the C ABI) and the CPU arm both "
+                    "run the same problem at 2^%d points (degree-%d hypercube graph): the host CSR of the full "
+                    "size is 32 GB" % (args.log2n, min(args.e2e_log2n, args.log2n), min(args.e2e_log2n, args.log2n))}
 
 
 def workload_name(log2n):
@@ -178,8 +190,30 @@ def workload_name(log2n):
 
 
 # ----------------------------------------------------------------------------------------------
+def pool_digest(local_pool, row0, rows, n, world, dist, dev):
+    """N-invariant fingerprint of the global minimiser pool: sha256 over the digests of the pool
+    restricted to fixed index blocks of 2^22 rows (a rank owns whole blocks), gathered in rank order."""
+    import hashlib
+    import numpy as np
+    import torch
+    blk = min(1 << 22, rows)
+    assert rows % blk == 0
+    edges = np.arange(row0, row0 + rows + 1, blk)
+    cut = np.searchsorted(local_pool, edges)
+    mine = b"".join(hashlib.sha256(np.ascontiguousarray(local_pool[cut[i]:cut[i + 1]]).tobytes()).digest()
+                    for i in range(len(edges) - 1))
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    if world > 1:
+        out = torch.empty(world * t.numel(), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        t = out
+    return hashlib.sha256(t.cpu().numpy().tobytes()).hexdigest()[:16]
+
+
 def main():
     args = parse()
+    if args.cpu_log2n is None:
+        args.cpu_log2n = min(args.e2e_log2n, args.log2n)
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -222,7 +256,8 @@ def main():
     # rows list i ^ 2^j in ascending j, so the neighbours owned by other GPUs (the top log2 N bits)
     # are the last entries of every row: the remote_at_ends promise of the sharded star test holds
     it = sdist.ShardedSobolIteration(fid, F.G_NONE, tab, n, row_ptr_l, col_l, exchange=args.exchange,
-                                     pool_cap=rows // 8, remote_at_ends=True)
+                                     pool_cap=rows // 8, remote_at_ends=True, chunks=args.chunks,
+                                     phase1_warps=args.phase1_warps)
     stream = torch.cuda.current_stream()
 
     def step(ev=None):
@@ -245,28 +280,37 @@ def main():
     for _ in range(40):
         step()
     barrier()
-    # per-kernel timing of the dominant kernel: a separate pass with events around it
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(4)]
-    for k in range(4):
-        step(evs[k])
-    barrier()
-    star_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    # Stage breakdown from events recorded INSIDE the timed region (start / after eval / after star
+    # of every step): eval + star + pool == step by construction.  At N > 1 the star stage of a rank
+    # includes its wait for the slowest peer's evaluation (the barrier), which is on that rank's
+    # critical path; the per-stage figures are averaged over ranks, the step time is the max.
     stream = torch.cuda.current_stream()
+    marks = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0.record(stream)
-    for _ in range(args.steps):
-        step()
+    for k in range(args.steps):
+        marks[k][0].record(stream)
+        step(marks[k][1:])
     t1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = t0.elapsed_time(t1)
-    tt = torch.tensor([ms_total, star_ms], dtype=torch.float64, device=dev)
+    ends = [marks[k + 1][0] for k in range(args.steps - 1)] + [t1]
+    eval_in = sum(m[0].elapsed_time(m[1]) for m in marks) / args.steps
+    star_ms = sum(m[1].elapsed_time(m[2]) for m in marks) / args.steps
+    pool_ms = sum(m[2].elapsed_time(e) for m, e in zip(marks, ends)) / args.steps
+    tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    stages = torch.tensor([eval_in, star_ms, pool_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stages)
+        stages /= world
     ms_step = float(tt[0].item()) / args.steps
-    star_ms = float(tt[1].item())
+    eval_in, star_ms, pool_ms = (float(x) for x in stages.tolist())
     value = n / (ms_step * 1e-3)
+    local_pool = it.local_pool().cpu().numpy()
+    pool_sha = pool_digest(local_pool, row0, rows, n, world, dist, dev)
     pc = torch.tensor([int(it.work.count[0].item()), int(it.nfev.item())], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(pc)
@@ -370,14 +414,21 @@ def main():
         return
 
     hbm_peak, peak_src = peaks()
+    # dram bytes of ONE launch of the dominant kernel from a committed `ncu --set full` capture; only
+    # quoted while the kernel source is the one that was profiled (sha of csrc/star.cu in the file)
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_star_traffic.json")
-    if os.path.exists(tp):           # dram bytes of ONE launch from a committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "r2_star_traffic.json")
+    if os.path.exists(tp):
+        import hashlib
         with open(tp) as fh:
             tj = json.load(fh)
-        if tj.get("log2n") == args.log2n and tj.get("n_gpus") == world:
+        with open(os.path.join(ROOT, "shgo_b200", "csrc", "star.cu"), "rb") as fh:
+            sha = hashlib.sha256(fh.read()).hexdigest()[:16]
+        if tj.get("log2n") == args.log2n and tj.get("n_gpus") == world and tj.get("star_cu_sha16") == sha:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
             traffic_src = tj["source"]
+        elif tj.get("log2n") == args.log2n and tj.get("n_gpus") == world:
+            traffic_src = "stale: csrc/star.cu changed since " + tj["source"]
     nnz_l = rows * m
     alg_bytes = 4 * nnz_l + 17 * rows
     achieved = alg_bytes / (star_ms * 1e-3) / 1e9
@@ -388,14 +439,17 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.log2n), "points": n, "rows_per_gpu": rows,
-                   "l2": "inputs (col = %.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
-                         % (nnz_l * 4 / 1e9),
-                   "exchange": {"p2p": "none: f shards peer-mapped over NVLink (CUDA IPC), neighbour "
-                                       "values read in place by the star kernel; 1 stream-ordered "
-                                       "barrier per step", "allgather": "nccl all_gather of f",
-                                "none": "none"}[args.exchange if world > 1 else "none"]},
-        "roofline": {"bound": "hbm", "kernel": "star_csr_kernel", "achieved": achieved,
+        "config": dict(config_of(args), rows_per_gpu=rows,
+                       l2="inputs (col = %.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
+                          % (nnz_l * 4 / 1e9),
+                       exchange={"fused": "none: f shards peer-mapped over NVLink (CUDA IPC); the star kernel "
+                                          "reads its candidates' remote neighbours in place, inline, once the "
+                                          "owner has published its shard; 1 stream-ordered barrier per step",
+                                 "p2p": "none: f shards peer-mapped over NVLink (CUDA IPC), neighbour "
+                                        "values read in place by a second kernel; 1 stream-ordered "
+                                        "barrier per step", "allgather": "nccl all_gather of f",
+                                 "none": "none"}[it.exchange]),
+        "roofline": {"bound": "hbm", "kernel": "star_kernel (csrc/star.cu)", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": star_ms},
@@ -403,8 +457,12 @@ def main():
                         "fp64_peak_measured_tflops": fp64_peak,
                         "frac_fp64": eval_tflops / fp64_peak if fp64_peak else None,
                         "hbm_write_gbs": 9 * rows / (eval_ms * 1e-3) / 1e9},
-        "pool_size": int(pc[0].item()), "nfev": int(pc[1].item()),
-        "gpu_launches": (KERNELS_PER_STEP + (1 if world > 1 and args.exchange == "p2p" else 0)) * args.steps,
+        "stages_ms": {"eval": eval_in, "star": star_ms, "pool": pool_ms,
+                      "note": "CUDA events inside the timed region, mean over steps and ranks; they add up "
+                              "to the mean step; at N > 1 the star stage includes the wait for the slowest "
+                              "peer's evaluation"},
+        "pool_size": int(pc[0].item()), "nfev": int(pc[1].item()), "pool_sha16": pool_sha,
+        "gpu_launches": (KERNELS_PER_STEP + {"fused": 2, "p2p": 1}.get(it.exchange, 0)) * args.steps,
         "clocks": clocks,
     }
     if e2e:

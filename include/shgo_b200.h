@@ -165,8 +165,13 @@ SHGO_B200_API int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t 
  * (NVLink bound) overlaps phase 1 of the next (HBM bound) on another stream.  flags / feasible are
  * indexed relative to row0, f_own relative to own0.
  * row_ptr / col are this shard's slices addressed with GLOBAL row ids / offsets (virtual bases).
- * remote_at_ends != 0 (same promise as for phase 2, see above): every row is trimmed to its local
- * middle part once and then walked like a single-GPU row, without a per-neighbour ownership test. */
+ * remote_at_ends bit 0 (same promise as for phase 2, see above): every row is trimmed to its local
+ * middle part once and then walked like a single-GPU row, without a per-neighbour ownership test.
+ * remote_at_ends bit 1 (shgo_b200_star_csr_local only): add to *nfev instead of overwriting it (the
+ * chunks of one shard accumulate into one counter).
+ * remote_at_ends bits 8..15 (shgo_b200_star_csr_local only): when non-zero, the most warps per SM the
+ * kernel may keep resident (default: as many as fit, 40) -- a caller that pipelines chunks leaves
+ * room this way for phase 2 of the previous chunk to run underneath on another stream. */
 SHGO_B200_API int shgo_b200_star_csr_local(const int64_t *row_ptr, const int32_t *col, const double *f_own,
                              const uint8_t *feasible, uint64_t own0, uint64_t own_rows,
                              uint64_t row0, uint64_t rows, uint64_t nnz_hint, int remote_at_ends,
@@ -179,6 +184,28 @@ SHGO_B200_API int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_
                               uint64_t rows_per_shard, int my_shard, uint64_t row0, uint64_t rows,
                               int remote_at_ends, uint8_t *flags, const void *cand_ws,
                               uint64_t cand_cap, void *tmp, size_t tmp_bytes, void *stream);
+/* Fused form of the two phases (round 2): phase 1 with remote_at_ends, and in the SAME kernel every
+ * candidate with at most 4 remote neighbours reads their f values in place over NVLink as soon as the
+ * owning GPUs have published their shard (ready[q] >= epoch, see shgo_b200_publish_ready); the loads
+ * are issued at the end of one tile and consumed at the end of the next, so the NVLink round trip
+ * hides behind the local work.  Candidates that could not be finished inline (peer not ready yet, more
+ * than 4 remote neighbours) keep flag 2 and are listed in cand_ws
+ * (required) for shgo_b200_star_csr_remote, which the caller runs after its barrier as before.
+ * Replaces the same reference code as shgo_b200_star_csr (_vertex.py:144-151, 422-426).
+ *   f_shards DEVICE array of nshards device pointers, nshards <= 16
+ *   ready   [nshards] uint32 in LOCAL device memory that the peers write (IPC-mapped on their side)
+ *   epoch   value that marks "written for this iteration" (the caller increments it per iteration) */
+SHGO_B200_API int shgo_b200_star_csr_fused(const int64_t *row_ptr, const int32_t *col,
+                             const double *const *f_shards, const double *f_own,
+                             const uint8_t *feasible, int nshards, uint64_t rows_per_shard,
+                             int my_shard, uint64_t row0, uint64_t rows, uint64_t nnz_hint,
+                             const uint32_t *ready, uint32_t epoch, uint8_t *flags, void *cand_ws,
+                             size_t cand_ws_bytes, uint64_t *nfev, void *stream);
+/* peer_flags: DEVICE array of npeers pointers, entry q = the `ready` array of GPU q (own or
+ * IPC-mapped); stores `epoch` into peer_flags[q][me] for every q with system-scope release
+ * semantics, stream-ordered after the kernels that wrote this GPU's shard of f. */
+SHGO_B200_API int shgo_b200_publish_ready(uint32_t *const *peer_flags, int npeers, int me, uint32_t epoch,
+                            void *stream);
 /* cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle / cudaFree;
  * handle64 is the 64-byte cudaIpcMemHandle_t to ship to the peer processes. */
 SHGO_B200_API int shgo_b200_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64);

@@ -1,357 +1,10 @@
-// graph.cu -- K3 (vertex-face mesh -> CSR), K4 (CSR star test), pool compaction, arg-min and
-// nfev bookkeeping.  Integer / byte work bound by HBM; no tensor cores involved.
+// graph.cu -- K3 (vertex-face mesh -> CSR), pool compaction, arg-min and nfev bookkeeping (the CSR
+// star test K4 lives in star.cu).  Integer / byte work bound by HBM; no tensor cores involved.
 #include <cstring>
 
 #include "common.cuh"
 
 namespace shgo_b200 {
-
-// =============================================================================================
-// K4: star test over an explicit CSR  (reference _vertex.py:144-151, 422-426)
-//
-// One WARP owns a tile of 32 consecutive rows; one thread walks one row.  The tile's slice of
-// `col` is the contiguous range col[row_ptr[r0] .. row_ptr[r0+32]) and is staged into the warp's
-// private shared-memory slice with 16-byte cp.async (LDGSTS) copies, so `col` -- 4*nnz bytes, the
-// bulk of the compulsory traffic -- streams from HBM exactly once at full sector efficiency and
-// without register staging.  Warps never wait on one another (only __syncwarp), so the 40 resident
-// warps of an SM are naturally staggered between "streaming col" and "gathering f".
-// The walk itself: neighbour ids come from shared memory, neighbour f values are gathered through
-// L1/L2 with ld.global.nc in rounds of 4, 8, then 16, 16, ...; a row stops as soon as one neighbour
-// is not strictly larger (the reference's all() short-circuits as well).  On a random field a row
-// survives k neighbours with probability 1/(k+1), so ~7 gathers per row are issued instead of deg,
-// while the widening rounds keep the dependent-latency chain of the few long-lived rows short
-// (measured: 4/8/16 beats 4/8/8 and 8/8/8 on lattice-like AND on random graphs, profiles/).
-// Mapping thread <-> row (not warp <-> row) makes the gathers of a warp hit neighbouring sectors
-// whenever consecutive rows have "parallel" neighbour lists (lattice-like graphs).
-// A tile whose slice exceeds the warp's staging buffer reads `col` from global memory instead.
-// The same pass counts nfev (rows that exist and are feasible, reference _vertex.py:184,347).
-// =============================================================================================
-constexpr int kStarWarps = 8;
-constexpr int kStarThreads = kStarWarps * 32;
-constexpr int kMaxStarWarps = 16384;  // upper bound on the warps of one star_csr_kernel launch
-
-// L2 policies: `col` and `row_ptr` are read exactly once -> evict_first, so that the 126 MB L2 is
-// spent on the f values the gathers come back for instead of on the 30 GB stream passing through.
-__device__ __forceinline__ uint64_t l2_evict_first_policy()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t l2_evict_last_policy()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, uint64_t pol)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ int64_t ld_stream_i64(const int64_t *p, uint64_t pol)
-{
-    int64_t v;
-    asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ double ld_keep_f64(const double *p, uint64_t pol)
-{
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-// gather of a neighbour's f: same policy, and an L2 miss fetches 64 instead of 128 bytes from DRAM
-// (ncu: 8 % less DRAM traffic on the bench graph; cudaLimitMaxL2FetchGranularity is ignored here)
-__device__ __forceinline__ double ld_gather_f64(const double *p, uint64_t pol)
-{
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.L2::64B.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-// One round of the row walk on the staged slice: the next W neighbours (32-bit local indices; the
-// tail of a row is handled by clamping, so a short row simply re-tests its last neighbour instead
-// of paying for per-entry predicates and +inf selects).
-// LOCAL (multi-GPU, phase 1): f is this GPU's shard, indexed by row - row0; neighbours owned by
-// another GPU are skipped here and remembered in `remote`.
-template <int W, bool LOCAL>
-__device__ __forceinline__ bool star_round(const int32_t *__restrict__ sc, const double *__restrict__ f,
-                                           double fv, int &k, int last, uint32_t row0, uint32_t rows,
-                                           bool &remote, uint64_t keep)
-{
-    int32_t nb[W];
-    double fn[W];
-#pragma unroll
-    for (int u = 0; u < W; ++u) nb[u] = sc[min(k + u, last)];
-#pragma unroll
-    for (int u = 0; u < W; ++u) {
-        if (LOCAL) {
-            const uint32_t l = (uint32_t)nb[u] - row0;
-            const bool mine = l < rows;
-            remote = remote || !mine;
-            fn[u] = mine ? ld_gather_f64(f + l, keep) : pos_inf();
-        } else {
-            fn[u] = ld_gather_f64(f + nb[u], keep);
-        }
-    }
-    bool ok = true;
-#pragma unroll
-    for (int u = 0; u < W; ++u) ok = ok && (fv < fn[u]);
-    k += W;
-    return ok;
-}
-
-struct StarMeta {  // what a lane knows about its row of a tile before the slice arrives
-    int64_t b, e;
-    double fv;
-    bool valid;
-};
-// f_rows: f addressed by GLOBAL row id (the caller passes the virtual base of a shard)
-__device__ __forceinline__ StarMeta star_meta(const int64_t *__restrict__ row_ptr,
-                                              const double *__restrict__ f_rows, uint64_t row0,
-                                              uint64_t rows, uint64_t tile, uint64_t ntiles, int lane,
-                                              uint64_t stream_pol, uint64_t keep)
-{
-    StarMeta m;
-    const uint64_t lr = (tile << 5) + lane;
-    m.valid = tile < ntiles && lr < rows;
-    const uint64_t r = row0 + (m.valid ? lr : rows);  // invalid lanes: empty row at the end
-    m.b = ld_stream_i64(row_ptr + r, stream_pol);
-    m.e = m.valid ? ld_stream_i64(row_ptr + r + 1, stream_pol) : m.b;
-    m.fv = m.valid ? ld_keep_f64(f_rows + r, keep) : 0.0;
-    return m;
-}
-
-// LOCAL = false: `f` is the whole vector, flags are 0 / 1.
-// LOCAL = true : `f` is this GPU's shard (rows row0 .. row0+rows); a row that passed every LOCAL
-//                neighbour but also has neighbours on other GPUs gets flag 2 ("candidate") and is
-//                finished by star_remote_kernel.
-// ENDS (LOCAL only): the caller promises that in every row the neighbours owned by other GPUs sit at
-// the two ends (ascending rows; the bench graph).  The row is trimmed to its local middle part once
-// and then walked exactly like a single-GPU row -- the per-neighbour ownership test of the general
-// LOCAL walk costs ~50 % more instructions per tile, 30 % of the kernel's time (ncu).
-template <bool LOCAL, bool ENDS>
-__global__ void __launch_bounds__(kStarThreads, 5)
-star_csr_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                const double *__restrict__ f, const uint8_t *__restrict__ feasible, uint64_t row0,
-                uint64_t rows, uint64_t own0, uint64_t own_rows, int cap_w,
-                uint8_t *__restrict__ is_min, uint32_t *__restrict__ cand_ws,
-                unsigned long long *__restrict__ nfev)
-{
-    extern __shared__ __align__(16) int32_t star_smem[];
-    const int lane = threadIdx.x & 31;
-    int32_t *sc = star_smem + (threadIdx.x >> 5) * cap_w;
-    const uint64_t ntiles = (rows + 31) >> 5;
-    const uint64_t gw = ((uint64_t)blockIdx.x * kStarThreads + threadIdx.x) >> 5;
-    const uint64_t nw = ((uint64_t)gridDim.x * kStarThreads) >> 5;
-    const double *f_rows = LOCAL ? f - own0 : f;  // LOCAL: f is the owned shard, rows own0 .. own0+own_rows
-    unsigned present_feasible = 0;
-    // LOCAL: every warp appends its candidates (flag 2) to a private, dense segment of cand_ws, so
-    // that phase 2 needs no compaction pass: [0] = warps, [1] = segment capacity, [2..2+kMaxStarWarps)
-    // = per-warp counts, then the segments
-    const uint32_t seg_cap = (uint32_t)(((ntiles + nw - 1) / nw) << 5);
-    uint32_t *seg = (LOCAL && cand_ws) ? cand_ws + 2 + kMaxStarWarps + gw * (uint64_t)seg_cap : nullptr;
-    uint32_t ncand = 0;
-    const uint64_t stream_pol = l2_evict_first_policy(), keep = l2_evict_last_policy();
-    // row_ptr / f of the NEXT tile are fetched while the current one is walked
-    StarMeta cur = star_meta(row_ptr, f_rows, row0, rows, gw, ntiles, lane, stream_pol, keep);
-    for (uint64_t tile = gw; tile < ntiles; tile += nw) {
-        const uint64_t lr = (tile << 5) + lane;
-        const int64_t b = cur.b, e = cur.e;
-        const double fv = cur.fv;
-        const bool valid = cur.valid;
-        const int64_t s0 = __shfl_sync(0xffffffffu, b, 0), s1 = __shfl_sync(0xffffffffu, e, 31);
-        // align the slice start down to a 16-byte ADDRESS (col may be a shard's virtual base)
-        const int64_t s0a = s0 - (int64_t)((reinterpret_cast<uintptr_t>(col + s0) >> 2) & 3);
-        const bool staged = s1 - s0a <= cap_w;
-        if (staged) {
-            const int len = (int)(s1 - s0a);
-            const int nvec = len >> 2;  // full 16-byte vectors inside the slice
-            const int32_t *src = col + s0a;
-            for (int v = lane; v < nvec; v += 32) cp_async16(sc + (v << 2), src + (v << 2), stream_pol);
-            for (int k = (nvec << 2) + lane; k < len; k += 32) sc[k] = __ldg(src + k);
-        }
-        cur = star_meta(row_ptr, f_rows, row0, rows, tile + nw, ntiles, lane, stream_pol, keep);
-        bool ok = valid && e > b;
-        bool remote = false;
-        if (nfev != nullptr && ok && (feasible == nullptr || feasible[lr])) ++present_feasible;
-        if (staged) {
-            cp_async_wait_all();
-            __syncwarp();
-            int k = (int)(b - s0a);
-            int le = (int)(e - s0a);
-            const uint32_t r0 = (uint32_t)own0, nr = (uint32_t)own_rows;
-            if (LOCAL && ENDS) {
-                const int k0 = k, le0 = le;
-                while (k < le && (uint32_t)sc[k] - r0 >= nr) ++k;
-                while (le > k && (uint32_t)sc[le - 1] - r0 >= nr) --le;
-                remote = k != k0 || le != le0;
-                const int last = le - 1;
-                // f_rows is addressed by GLOBAL row id, like f of the single-GPU kernel
-                if (ok && k < le) ok = star_round<4, false>(sc, f_rows, fv, k, last, r0, nr, remote, keep);
-                if (ok && k < le) ok = star_round<8, false>(sc, f_rows, fv, k, last, r0, nr, remote, keep);
-                while (ok && k < le) ok = star_round<16, false>(sc, f_rows, fv, k, last, r0, nr, remote, keep);
-            } else {
-                const int last = le - 1;
-                if (ok) ok = star_round<4, LOCAL>(sc, f, fv, k, last, r0, nr, remote, keep);
-                if (ok && k < le) ok = star_round<8, LOCAL>(sc, f, fv, k, last, r0, nr, remote, keep);
-                while (ok && k < le) ok = star_round<16, LOCAL>(sc, f, fv, k, last, r0, nr, remote, keep);
-            }
-        } else {
-            for (int64_t k = b; k < e && ok; ++k) {
-                const int32_t w = __ldg(col + k);
-                if (LOCAL) {
-                    const uint32_t l = (uint32_t)w - (uint32_t)own0;
-                    if (l < (uint32_t)own_rows) ok = fv < ld_nc_f64(f + l); else remote = true;
-                } else {
-                    ok = fv < ld_nc_f64(f + w);
-                }
-            }
-        }
-        const bool candidate = LOCAL && valid && ok && remote;
-        if (valid) is_min[lr] = ok ? (candidate ? 2 : 1) : 0;
-        if (LOCAL && seg != nullptr) {
-            const unsigned m = __ballot_sync(0xffffffffu, candidate);
-            if (candidate) seg[ncand + __popc(m & ((1u << lane) - 1u))] = (uint32_t)lr;
-            ncand += __popc(m);
-        }
-        __syncwarp();  // the slice is rewritten by the next tile
-    }
-    if (LOCAL && seg != nullptr && lane == 0) {
-        cand_ws[2 + gw] = ncand;
-        if (gw == 0) {
-            cand_ws[0] = (uint32_t)nw;
-            cand_ws[1] = seg_cap;
-        }
-    }
-    if (nfev != nullptr) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) present_feasible += __shfl_down_sync(0xffffffffu, present_feasible, o);
-        if (lane == 0 && present_feasible) atomicAdd(nfev, (unsigned long long)present_feasible);
-    }
-}
-
-// ---- multi-GPU, phase 2 ---------------------------------------------------------------------------
-// f lives in N equal shards, one per GPU, all mapped into this process over NVLink (CUDA IPC).
-// One thread per CANDIDATE row (compacted list: a few percent of the rows) re-reads its neighbour
-// list and tests only the neighbours owned by other GPUs, reading their f in place through the
-// peer pointers -- plain ld.global over NVLink, all candidates in flight at once, so the link
-// latency is hidden by parallelism and only 8 bytes per remote neighbour of a candidate cross it.
-struct ShardedF {
-    const double *const *shards;  // device array of nshards base pointers (own shard = local HBM)
-    uint32_t rows_per_shard;
-    __device__ __forceinline__ double operator()(int32_t w) const
-    {
-        const uint32_t q = (uint32_t)w / rows_per_shard;
-        const double *p = shards[q] + ((uint32_t)w - q * rows_per_shard);
-        double v;
-        asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
-        return v;
-    }
-};
-
-__device__ __forceinline__ void star_remote_one(uint64_t lr, const int64_t *__restrict__ row_ptr,
-                                                const int32_t *__restrict__ col, const ShardedF &facc,
-                                                const double *__restrict__ f_own, uint64_t own0,
-                                                uint64_t own_rows, uint64_t row0, int remote_at_ends,
-                                                uint8_t *__restrict__ is_min)
-{
-    const uint64_t r = row0 + lr;
-    const double fv = ld_nc_f64(f_own + (r - own0));
-    bool ok = true;
-    const int64_t b = row_ptr[r], e = row_ptr[r + 1];
-    const uint32_t o0 = (uint32_t)own0, on = (uint32_t)own_rows;
-    if (remote_at_ends) {
-        // Promise of the caller: the neighbours owned by other GPUs sit at the two ENDS of the
-        // row (e.g. ascending rows: ids below own0 first, ids >= own0+own_rows last).  Read four entries from each end together and
-        // fetch the remote ones' values over NVLink: two latency round trips and two sectors of
-        // `col` per candidate instead of a walk over the whole row.  A side whose four entries
-        // are all remote is continued inwards.
-        int64_t klo = b, khi = e;  // [klo, khi) is what has not been looked at yet
-        bool more_lo = true, more_hi = true;
-        while (ok && klo < khi && (more_lo || more_hi)) {
-            int32_t w[8];
-            bool use[8];
-            double fn[8];
-            const int64_t nlo = more_lo ? min((int64_t)4, khi - klo) : 0;
-            const int64_t nhi = more_hi ? min((int64_t)4, khi - klo - nlo) : 0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                w[u] = u < nlo ? __ldg(col + klo + u) : 0;
-                w[4 + u] = u < nhi ? __ldg(col + khi - 1 - u) : 0;
-            }
-            bool all_lo = nlo == 4, all_hi = nhi == 4;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                use[u] = u < nlo && ((uint32_t)w[u] - o0 >= on);
-                use[4 + u] = u < nhi && ((uint32_t)w[4 + u] - o0 >= on);
-                all_lo = all_lo && (use[u] || u >= nlo);
-                all_hi = all_hi && (use[4 + u] || u >= nhi);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) fn[u] = use[u] ? facc(w[u]) : pos_inf();
-#pragma unroll
-            for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
-            klo += nlo;
-            khi -= nhi;
-            more_lo = more_lo && all_lo;
-            more_hi = more_hi && all_hi;
-        }
-    } else {
-        // 8 neighbour ids, then their (remote only) f values, are in flight together
-        for (int64_t k = b; k < e && ok; k += 8) {
-            int32_t w[8];
-            double fn[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) w[u] = __ldg(col + (k + u < e ? k + u : e - 1));
-#pragma unroll
-            for (int u = 0; u < 8; ++u) fn[u] = ((uint32_t)w[u] - o0 < on) ? pos_inf() : facc(w[u]);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
-        }
-    }
-    is_min[lr] = ok ? 1 : 0;
-}
-
-// candidates from a compacted index list (phase 1 ran without a candidate workspace)
-__global__ void __launch_bounds__(256)
-star_remote_kernel(const int64_t *__restrict__ cand, const uint64_t *__restrict__ ncand, uint64_t cap,
-                   const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col, ShardedF facc,
-                   const double *__restrict__ f_own, uint64_t own0, uint64_t own_rows, uint64_t row0,
-                   int remote_at_ends, uint8_t *__restrict__ is_min)
-{
-    uint64_t n = *ncand;
-    if (n > cap) n = cap;
-    for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n;
-         c += (uint64_t)gridDim.x * blockDim.x)
-        star_remote_one((uint64_t)cand[c], row_ptr, col, facc, f_own, own0, own_rows, row0, remote_at_ends,
-                        is_min);
-}
-
-// candidates from the per-warp segments phase 1 wrote: no compaction pass in between
-__global__ void __launch_bounds__(256)
-star_remote_seg_kernel(const uint32_t *__restrict__ cand_ws, const int64_t *__restrict__ row_ptr,
-                       const int32_t *__restrict__ col, ShardedF facc, const double *__restrict__ f_own,
-                       uint64_t own0, uint64_t own_rows, uint64_t row0, int remote_at_ends,
-                       uint8_t *__restrict__ is_min)
-{
-    const uint32_t nw = cand_ws[0], seg_cap = cand_ws[1];
-    const int lane = threadIdx.x & 31;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t sw = gw; sw < nw; sw += tw) {
-        const uint32_t n = cand_ws[2 + sw];
-        const uint32_t *seg = cand_ws + 2 + kMaxStarWarps + sw * (uint64_t)seg_cap;
-        for (uint32_t i = lane; i < n; i += 32)
-            star_remote_one((uint64_t)seg[i], row_ptr, col, facc, f_own, own0, own_rows, row0, remote_at_ends,
-                            is_min);
-    }
-}
 
 // =============================================================================================
 // Multi-block exclusive scan of small counts (uint8 flags or uint32 degrees) into 64-bit offsets.
@@ -733,47 +386,6 @@ static inline unsigned grid_for(uint64_t items, int threads, int per_sm)
 
 using namespace shgo_b200;
 
-static size_t star_smem_bytes(uint64_t rows, uint64_t nnz_hint, long *cap_out)
-{
-    // staging slice per warp: 32 rows * ~1.125 * mean degree (+ alignment slack), 16-byte multiple
-    double mean_deg = nnz_hint ? (double)nnz_hint / (double)rows : 32.0;
-    long cap = (long)(mean_deg * 32.0 * 1.125) + 16;
-    if (cap < 256) cap = 256;
-    if (cap > 6144) cap = 6144;  // 24 KB per warp at most (1 CTA of 8 warps per SM)
-    cap = (cap + 63) & ~63L;
-    *cap_out = cap;
-    return (size_t)cap * kStarWarps * sizeof(int32_t);
-}
-
-template <bool LOCAL, bool ENDS = false>
-static int launch_star(const int64_t *row_ptr, const int32_t *col, const double *f,
-                       const uint8_t *feasible, uint64_t row0, uint64_t rows, uint64_t own0,
-                       uint64_t own_rows, uint64_t nnz_hint, uint8_t *is_min, uint32_t *cand_ws,
-                       uint64_t *nfev, cudaStream_t st)
-{
-    if (nfev) SHGO_CUDA_TRY(cudaMemsetAsync(nfev, 0, sizeof(uint64_t), st));
-    if (rows == 0) return SHGO_B200_OK;
-    SHGO_REQUIRE(row_ptr && f && is_min, "null pointer");
-    SHGO_REQUIRE((reinterpret_cast<uintptr_t>(col) & 3) == 0, "col must be 4-byte aligned");
-    long cap = 0;
-    const size_t smem = star_smem_bytes(rows, nnz_hint, &cap);
-    auto kern = star_csr_kernel<LOCAL, ENDS>;
-    if (smem > 48 * 1024)
-        SHGO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    int occ = 0;
-    SHGO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kStarThreads, smem));
-    if (occ < 1) occ = 1;
-    uint64_t tiles = (rows + kStarThreads - 1) / kStarThreads;
-    uint64_t grid = (uint64_t)sm_count() * occ;
-    if (grid > tiles) grid = tiles;
-    if (grid * kStarWarps > (uint64_t)kMaxStarWarps) grid = kMaxStarWarps / kStarWarps;
-    kern<<<(unsigned)grid, kStarThreads, smem, st>>>(row_ptr, col, f, feasible, row0, rows, own0, own_rows,
-                                                    (int)cap, is_min, cand_ws,
-                                                    reinterpret_cast<unsigned long long *>(nfev));
-    SHGO_CUDA_TRY(cudaGetLastError());
-    return SHGO_B200_OK;
-}
-
 int shgo_b200::compact_flags(const uint8_t *flags, uint64_t n, int match, int64_t base, int64_t *idx_out,
                              uint64_t cap, uint64_t *count, void *tmp, cudaStream_t st)
 {
@@ -791,93 +403,6 @@ int shgo_b200::compact_flags(const uint8_t *flags, uint64_t n, int match, int64_
 }
 
 extern "C" {
-
-int shgo_b200_star_csr(const int64_t *row_ptr, const int32_t *col, const double *f, uint64_t row0,
-                       uint64_t rows, uint64_t nnz_hint, uint8_t *is_min, void *stream)
-{
-    return launch_star<false>(row_ptr, col, f, nullptr, row0, rows, 0, 0, nnz_hint, is_min, nullptr, nullptr,
-                              as_stream(stream));
-}
-
-int shgo_b200_star_csr_nfev(const int64_t *row_ptr, const int32_t *col, const double *f,
-                            const uint8_t *feasible, uint64_t row0, uint64_t rows, uint64_t nnz_hint,
-                            uint8_t *is_min, uint64_t *nfev, void *stream)
-{
-    SHGO_REQUIRE(nfev, "null nfev");
-    return launch_star<false>(row_ptr, col, f, feasible, row0, rows, 0, 0, nnz_hint, is_min, nullptr, nfev,
-                              as_stream(stream));
-}
-
-int shgo_b200_star_csr_local(const int64_t *row_ptr, const int32_t *col, const double *f_own,
-                             const uint8_t *feasible, uint64_t own0, uint64_t own_rows, uint64_t row0,
-                             uint64_t rows, uint64_t nnz_hint, int remote_at_ends, uint8_t *flags,
-                             void *cand_ws, size_t cand_ws_bytes, uint64_t *nfev, void *stream)
-{
-    SHGO_REQUIRE(own0 + own_rows <= 0x7fffffffull, "row range out of int32");
-    SHGO_REQUIRE(row0 >= own0 && row0 + rows <= own0 + own_rows, "classified rows outside the owned shard");
-    if (cand_ws && cand_ws_bytes < shgo_b200_star_local_workspace(rows))
-        return fail(SHGO_B200_ERR_WORKSPACE, "candidate workspace: need %zu bytes, got %zu",
-                    shgo_b200_star_local_workspace(rows), cand_ws_bytes);
-    if (remote_at_ends)
-        return launch_star<true, true>(row_ptr, col, f_own, feasible, row0, rows, own0, own_rows, nnz_hint,
-                                       flags, static_cast<uint32_t *>(cand_ws), nfev, as_stream(stream));
-    return launch_star<true>(row_ptr, col, f_own, feasible, row0, rows, own0, own_rows, nnz_hint, flags,
-                             static_cast<uint32_t *>(cand_ws), nfev, as_stream(stream));
-}
-
-size_t shgo_b200_star_local_workspace(uint64_t rows)
-{
-    // header + per-warp counts + per-warp segments (each rounded up to whole tiles of 32 rows)
-    return align256((2 + (size_t)kMaxStarWarps + rows + 32ull * kMaxStarWarps) * sizeof(uint32_t));
-}
-
-size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap)
-{
-    return align256(cand_cap * sizeof(int64_t)) + shgo_b200_compact_workspace(rows) + align256(16);
-}
-
-int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const double *const *f_shards,
-                              const double *f_own, int nshards, uint64_t rows_per_shard, int my_shard,
-                              uint64_t row0, uint64_t rows, int remote_at_ends, uint8_t *flags,
-                              const void *cand_ws, uint64_t cand_cap, void *tmp, size_t tmp_bytes,
-                              void *stream)
-{
-    cudaStream_t st = as_stream(stream);
-    if (rows == 0) return SHGO_B200_OK;
-    SHGO_REQUIRE(row_ptr && f_shards && f_own && flags && (tmp || cand_ws), "null pointer");
-    SHGO_REQUIRE(nshards >= 1 && my_shard >= 0 && my_shard < nshards, "bad shard index");
-    SHGO_REQUIRE(rows_per_shard >= 1 && rows_per_shard <= 0x7fffffffull, "bad shard size");
-    const uint64_t own0 = (uint64_t)my_shard * rows_per_shard;
-    SHGO_REQUIRE(row0 >= own0 && row0 + rows <= own0 + rows_per_shard, "classified rows outside the owned shard");
-    if (cand_ws) {  // phase 1 already listed the candidates
-        ShardedF fa{f_shards, (uint32_t)rows_per_shard};
-        star_remote_seg_kernel<<<sm_count() * 8, 256, 0, st>>>(static_cast<const uint32_t *>(cand_ws), row_ptr, col,
-                                                             fa, f_own, own0, rows_per_shard, row0,
-                                                             remote_at_ends, flags);
-        SHGO_CUDA_TRY(cudaGetLastError());
-        return SHGO_B200_OK;
-    }
-    if (tmp_bytes < shgo_b200_star_remote_workspace(rows, cand_cap))
-        return fail(SHGO_B200_ERR_WORKSPACE, "remote-phase workspace: need %zu bytes, got %zu",
-                    shgo_b200_star_remote_workspace(rows, cand_cap), tmp_bytes);
-    unsigned char *p = static_cast<unsigned char *>(tmp);
-    int64_t *cand = reinterpret_cast<int64_t *>(p);
-    p += align256(cand_cap * sizeof(int64_t));
-    void *ctmp = p;
-    p += shgo_b200_compact_workspace(rows);
-    uint64_t *ncand = reinterpret_cast<uint64_t *>(p);
-    if (int rc = compact_flags(flags, rows, /*match=*/2, 0, cand, cand_cap, ncand, ctmp, st)) return rc;
-    ShardedF facc{f_shards, (uint32_t)rows_per_shard};
-    // candidates beyond cand_cap would be left with flag 2; callers size cand_cap = rows to be safe
-    uint64_t blocks = (rows / 16 + 255) / 256;  // ~ one thread per expected candidate, capped
-    const uint64_t capb = (uint64_t)sm_count() * 8;
-    if (blocks > capb) blocks = capb;
-    if (blocks < 1) blocks = 1;
-    star_remote_kernel<<<(unsigned)blocks, 256, 0, st>>>(cand, ncand, cand_cap, row_ptr, col, facc, f_own, own0,
-                                                        rows_per_shard, row0, remote_at_ends, flags);
-    SHGO_CUDA_TRY(cudaGetLastError());
-    return SHGO_B200_OK;
-}
 
 // ---- CUDA IPC plumbing for the peer-mapped f shards ---------------------------------------------
 int shgo_b200_ipc_alloc(size_t bytes, void **ptr, unsigned char *handle64)

@@ -4,12 +4,19 @@ SURVEY.md section 8(e): rank r of G owns Sobol indices / graph rows [r n/G, (r+1
 has a closed-form skip-ahead, so every shard generates and evaluates locally with no communication.
 The star test needs neighbours' f across shards.  Two exchanges are implemented:
 
-  'p2p'        (default on GPUs) the f shards are allocated with cudaMalloc, exported with CUDA IPC and
+  'p2p'        the f shards are allocated with cudaMalloc, exported with CUDA IPC and
                peer-mapped into every rank over NVLink.  Phase 1 classifies every row against its
                LOCAL neighbours (no communication); phase 2 finishes the few rows that survived --
                their remote neighbours' f values are read in place over NVLink by the kernel itself,
                8 bytes per remote neighbour of a candidate.  Collectives are used for plumbing only
                (one stream-ordered barrier per iteration, pool gather).
+  'fused'      (default on GPUs when remote neighbours sit at the row ends) the same data path in ONE
+               kernel: every rank publishes "my shard is written" into a flag word of every peer
+               right after its evaluation, and the star kernel reads the remote neighbours of its
+               candidates in place over NVLink as soon as the owner's flag is up -- issued at the
+               end of one tile, consumed at the end of the next, so the NVLink round trip hides
+               behind the local classification.  What was met before a peer was ready is finished by
+               the phase-2 kernel after the barrier, as in 'p2p'.
   'allgather'  one all_gather of the f vector (NCCL on GPUs; gloo in the CPU tests), then the
                single-GPU star kernel on the rank's rows.  8 n (G-1)/G bytes received per GPU.
 
@@ -34,16 +41,17 @@ class _RawCudaBuffer:
 
 
 class PeerMappedVector:
-    """A float64 vector of `rows` elements per rank, readable by every rank's kernels."""
+    """A vector of `rows` elements per rank (float64, or int32 words with typestr '<i4'), readable
+    and writable by every rank's kernels (cudaMalloc + CUDA IPC, mapped over NVLink)."""
 
-    def __init__(self, rows, group=None):
+    def __init__(self, rows, group=None, typestr="<f8"):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.rows = rows
         ptr = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * 64)()
-        _lib.call("shgo_b200_ipc_alloc", rows * 8, ctypes.byref(ptr), handle)
+        _lib.call("shgo_b200_ipc_alloc", max(rows * int(typestr[2:]), 256), ctypes.byref(ptr), handle)
         self.own_ptr = ptr.value
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle), group=group)
@@ -60,7 +68,7 @@ class PeerMappedVector:
                 self._opened.append(p.value)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.table = torch.tensor(self.peer_ptrs, dtype=torch.int64, device=dev)
-        self.local = torch.as_tensor(_RawCudaBuffer(self.own_ptr, rows, "<f8"), device=dev)
+        self.local = torch.as_tensor(_RawCudaBuffer(self.own_ptr, rows, typestr), device=dev)
 
     def close(self):
         torch.cuda.synchronize()
@@ -97,8 +105,8 @@ class ShardedSobolIteration:
     row_ptr[row0] (i.e. a slice of the global row_ptr), col_local the matching slice of col with
     GLOBAL vertex ids."""
 
-    def __init__(self, functor, gset, tab, n, row_ptr_local, col_local, group=None, exchange="p2p",
-                 pool_cap=None, chunks=1, remote_at_ends=False):
+    def __init__(self, functor, gset, tab, n, row_ptr_local, col_local, group=None, exchange="fused",
+                 pool_cap=None, remote_at_ends=False, chunks=1, phase1_warps=0):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -120,7 +128,9 @@ class ShardedSobolIteration:
         # (true for ascending rows, i.e. for every CSR built by csr_from_simplices)
         self.remote_at_ends = bool(remote_at_ends)
         self._k = 0
-        if self.exchange == "p2p":
+        if self.exchange == "fused" and not self.remote_at_ends:
+            self.exchange = "p2p"      # the fused kernel needs the remote_at_ends promise
+        if self.exchange in ("p2p", "fused"):
             # two peer-mapped buffers used alternately: iteration k+1 writes the other buffer while
             # slow peers may still be reading buffer k, so ONE barrier per iteration is enough
             # (a rank passes barrier k+1 only after every peer has finished its reads of step k)
@@ -131,19 +141,29 @@ class ShardedSobolIteration:
             ws = _lib.lib().shgo_b200_star_remote_workspace(self.rows, self.rows)
             self._remote_tmp = torch.empty(ws, dtype=torch.uint8, device=dev)
             # phase 1 lists its candidates here, phase 2 consumes the list (no compaction pass)
-            # one list per chunk: phase 2 of chunk c reads its list on the `_remote` stream while
-            # phase 1 of chunk c+1 is already writing the next one on the main stream
-            self.chunks = max(1, int(chunks))
-            per = self.rows // self.chunks
-            self._chunk_rows = [per if c < self.chunks - 1 else self.rows - c * per for c in range(self.chunks)]
-            self._cand_ws = [torch.empty(_lib.lib().shgo_b200_star_local_workspace(nr), dtype=torch.uint8,
-                                         device=dev) for nr in self._chunk_rows]
+            self._cand_ws = torch.empty(_lib.lib().shgo_b200_star_local_workspace(self.rows), dtype=torch.uint8,
+                                        device=dev)
             self._comm = torch.cuda.Stream(device=dev)
-            self._remote = torch.cuda.Stream(device=dev)
-            # chunks > 1 pipelines phase 2 of one chunk under phase 1 of the next on a second stream;
-            # measured on B200 it does not pay (the persistent phase-1 kernel leaves no room for the
-            # phase-2 CTAs to co-run), so the default is a single chunk
-            self._nfev_parts = torch.zeros(self.chunks, dtype=torch.int64, device=dev)
+            # 'p2p' with chunks > 1: the rows are classified in chunks; phase 2 of chunk c (bound by the
+            # rate of small NVLink reads) runs on a second stream underneath phase 1 of chunk c+1
+            # (bound by HBM), which keeps at most `phase1_warps` warps per SM resident so that the
+            # phase-2 blocks find room.  One candidate list per chunk (phase 2 of chunk c reads its list
+            # while phase 1 of chunk c+1 writes the next).
+            self.chunks = max(1, int(chunks)) if self.exchange == "p2p" else 1
+            self.phase1_warps = int(phase1_warps) if self.chunks > 1 else 0
+            per = (self.rows // self.chunks) & ~31
+            self._chunk_rows = [per if c < self.chunks - 1 else self.rows - c * per for c in range(self.chunks)]
+            if self.chunks > 1:
+                self._remote = torch.cuda.Stream(device=dev)
+                self._cand_ws = [torch.empty(_lib.lib().shgo_b200_star_local_workspace(nr), dtype=torch.uint8,
+                                             device=dev) for nr in self._chunk_rows]
+
+            if self.exchange == "fused":
+                # ready[q] on this rank = last iteration whose shard rank q has completely written
+                self._ready = PeerMappedVector(max(self.world, 64), group, typestr="<i4")
+                self._ready.local.zero_()
+                torch.cuda.synchronize()
+                dist.barrier(group=group)
         else:
             self.f_all = torch.empty(n if self.world > 1 else self.rows, dtype=torch.float64, device=dev)
             self.f_my = self.f_all[self.row0:self.row0 + self.rows] if self.world > 1 else self.f_all
@@ -162,34 +182,53 @@ class ShardedSobolIteration:
 
     def step(self, events=None):
         """One iteration; free of host synchronisation (capturable in a CUDA graph)."""
-        if self.exchange == "p2p":
+        if self.peer is not None:
             self.peer = self.peers[self._k & 1]
             self.f_my = self.peer.local
             self._k += 1
         hp.eval_sobol(self.functor, self.gset, self.tab, self.row0, self.rows, f=self.f_my, feasible=self.feas)
         if events:
             events[0].record()
-        if self.exchange == "p2p":
-            # Phase 1 needs nobody else; the barrier (every shard of f complete before anyone reads
-            # it remotely) runs concurrently with it on a side stream.  The rows are classified in
-            # chunks so that phase 2 of a chunk -- bound by the rate of small NVLink reads -- runs on
-            # a second stream underneath phase 1 of the next chunk, which is bound by HBM.
+        if self.exchange == "fused":
+            # tell every peer that this shard is written, then classify: candidates read their
+            # remote neighbours in place inside the kernel once the owner's word is up.  The barrier
+            # (for what the kernel met too early, and for the reuse of the f buffers) runs on the
+            # side stream underneath.
+            hp.publish_ready(self._ready.table, self.world, self.rank, self._k)
+            self._barrier_async()
+            hp.star_csr_fused(self.row_ptr, self.col, self.row0, self.peer.table, self.f_my, self.feas, self.world,
+                              self.rows, self.rank, self._ready.local, self._k, self.is_min, self._cand_ws,
+                              self.nfev, self.off0)
+            self._barrier_wait()
+            hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table, self.peer.own_ptr, self.world,
+                               self.rows, self.rank, self.is_min, None, self.off0, remote_at_ends=True,
+                               cand_ws=self._cand_ws)
+        elif self.exchange == "p2p" and self.chunks > 1:
             self._barrier_async()
             main = torch.cuda.current_stream()
             self._remote.wait_stream(self._comm)
             r0 = self.row0
             for c, nr in enumerate(self._chunk_rows):
                 hp.star_csr_local(self.row_ptr, self.col, self.row0, self.f_my, self.feas, self.is_min,
-                                  self._nfev_parts[c:c + 1], self.off0, r0, nr, self._cand_ws[c], self.remote_at_ends)
+                                  self.nfev, self.off0, r0, nr, self._cand_ws[c], self.remote_at_ends,
+                                  max_warps=self.phase1_warps, accumulate_nfev=c > 0)
                 self._remote.wait_stream(main)
                 with torch.cuda.stream(self._remote):
-                    hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table,
-                                       self.peer.own_ptr, self.world, self.rows, self.rank, self.is_min,
-                                       self._remote_tmp, self.off0, r0, nr, self.remote_at_ends,
-                                       self._cand_ws[c])
+                    hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table, self.peer.own_ptr,
+                                       self.world, self.rows, self.rank, self.is_min, None, self.off0, r0, nr,
+                                       self.remote_at_ends, self._cand_ws[c])
                 r0 += nr
             main.wait_stream(self._remote)
-            torch.sum(self._nfev_parts, 0, keepdim=True, out=self.nfev)
+        elif self.exchange == "p2p":
+            # Phase 1 needs nobody else; the barrier (every shard of f complete before anyone reads
+            # it remotely) runs concurrently with it on a side stream.
+            self._barrier_async()
+            hp.star_csr_local(self.row_ptr, self.col, self.row0, self.f_my, self.feas, self.is_min, self.nfev,
+                              self.off0, cand_ws=self._cand_ws, remote_at_ends=self.remote_at_ends)
+            self._barrier_wait()
+            hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table, self.peer.own_ptr, self.world,
+                               self.rows, self.rank, self.is_min, self._remote_tmp, self.off0,
+                               remote_at_ends=self.remote_at_ends, cand_ws=self._cand_ws)
         else:
             if self.exchange == "allgather":
                 _all_gather(self.f_all, self.f_my, self.group)
@@ -227,6 +266,8 @@ class ShardedSobolIteration:
         if self.peer is not None:
             for p in self.peers:
                 p.close()
+            if self.exchange == "fused":
+                self._ready.close()
             self.peer = None
             self.peers = []
 

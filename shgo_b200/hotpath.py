@@ -197,7 +197,7 @@ def star_csr_shard(row_ptr_local, col_local, row0, f_all, feasible, is_min, nfev
 
 
 def star_csr_local(row_ptr_local, col_local, own0, f_own, feasible, flags, nfev, off0=None, r0=None,
-                   nrows=None, cand_ws=None, remote_at_ends=False):
+                   nrows=None, cand_ws=None, remote_at_ends=False, max_warps=0, accumulate_nfev=False):
     """Multi-GPU phase 1: rows [r0, r0+nrows) of this GPU's shard (default: all of it) against its
     OWN shard of f; flags 0 / 1 / 2 (candidate).  feasible / flags are whole-shard tensors.
     remote_at_ends: promise that other GPUs' vertices sit at the two ends of every row (faster walk)."""
@@ -211,7 +211,8 @@ def star_csr_local(row_ptr_local, col_local, own0, f_own, feasible, flags, nfev,
     _lib.call("shgo_b200_star_csr_local", row_ptr_local.data_ptr() - own0 * 8,
               col_local.data_ptr() - off0 * 4, _ptr(f_own),
               feasible.data_ptr() + sh if feasible is not None else None, own0, own_rows, r0, nrows, hint,
-              1 if remote_at_ends else 0, flags.data_ptr() + sh, _ptr(cand_ws), cand_ws.numel() if cand_ws is not None else 0, _ptr(nfev),
+              (1 if remote_at_ends else 0) | (2 if accumulate_nfev else 0) | (int(max_warps) << 8), flags.data_ptr() + sh, _ptr(cand_ws),
+              cand_ws.numel() if cand_ws is not None else 0, _ptr(nfev),
               _stream())
     return flags
 
@@ -232,6 +233,31 @@ def star_csr_remote(row_ptr_local, col_local, own0, peer_table, f_own_ptr, nshar
               my_shard, r0, nrows, 1 if remote_at_ends else 0, flags.data_ptr() + (r0 - own0), _ptr(cand_ws),
               nrows, _ptr(tmp), tmp.numel() if tmp is not None else 0, _stream())
     return flags
+
+
+def star_csr_fused(row_ptr_local, col_local, own0, peer_table, f_own, feasible, nshards, rows_per_shard,
+                   my_shard, ready, epoch, flags, cand_ws, nfev, off0=None, r0=None, nrows=None):
+    """Multi-GPU phases 1 + 2 in one kernel (remote_at_ends promise required): candidates whose peers
+    have published their shard (ready[q] >= epoch) read the remote f values in place over NVLink
+    from inside the kernel; the rest keep flag 2 and are listed in cand_ws for star_csr_remote."""
+    own_rows = row_ptr_local.numel() - 1
+    if off0 is None:
+        off0 = int(row_ptr_local[0].item())
+    r0 = own0 if r0 is None else r0
+    nrows = own_rows if nrows is None else nrows
+    sh = r0 - own0
+    hint = col_local.numel() * nrows // max(own_rows, 1)
+    _lib.call("shgo_b200_star_csr_fused", row_ptr_local.data_ptr() - own0 * 8, col_local.data_ptr() - off0 * 4,
+              _ptr(peer_table), _ptr(f_own), feasible.data_ptr() + sh if feasible is not None else None,
+              nshards, rows_per_shard, my_shard, r0, nrows, hint, _ptr(ready), epoch,
+              flags.data_ptr() + sh, _ptr(cand_ws), cand_ws.numel(), _ptr(nfev), _stream())
+    return flags
+
+
+def publish_ready(flag_table, npeers, me, epoch):
+    """Store `epoch` into every peer's ready[me] (flag_table: device int64 tensor of the peers' flag
+    array addresses), stream-ordered after the evaluation that wrote this GPU's shard of f."""
+    _lib.call("shgo_b200_publish_ready", _ptr(flag_table), npeers, me, epoch, _stream())
 
 
 class PoolWorkspace:

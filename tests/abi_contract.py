@@ -106,6 +106,19 @@ def shgo_b200_star_csr_remote(row_ptr, col, f_shards, f_own, nshards, rows_per_s
     _req(row0 >= own0 and row0 + rows <= own0 + rows_per_shard, "classified rows outside the owned shard")
 
 
+def shgo_b200_star_csr_fused(row_ptr, col, f_shards, f_own, feasible, nshards, rows_per_shard, my_shard, row0, rows,
+                             nnz_hint, ready, epoch, flags, cand_ws, cand_ws_bytes, nfev, stream):
+    _req(f_shards and f_own and ready and cand_ws, "null pointer")
+    _req(nshards >= 1 and 0 <= my_shard < nshards, "bad shard index")
+    _req(rows_per_shard >= 1 and rows_per_shard * nshards <= 0x7fffffff, "bad shard size")
+    own0 = my_shard * rows_per_shard
+    _req(row0 >= own0 and row0 + rows <= own0 + rows_per_shard, "classified rows outside the owned shard")
+
+
+def shgo_b200_publish_ready(peer_flags, npeers, me, epoch, stream):
+    _req(peer_flags and 1 <= npeers <= 32 and me >= 0, "bad arguments")
+
+
 def shgo_b200_compact_pool(is_min, n, base, idx_out, cap, count, tmp, tmp_bytes, stream):
     _req(count and tmp, "null pointer")
     _req(is_min or n == 0, "null flags")

@@ -511,6 +511,29 @@ def test_two_phase_sharded_star_emulated_on_one_gpu(hp, nshards):
             hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, fl4, None,
                                remote_at_ends=True, cand_ws=cws)
             assert torch.equal(fl4, flags)
+            # phases 1 + 2 fused in one kernel: peers all ready / none ready / some ready
+            for ready_mask in (None, 0, 0b10101010):
+                epoch = 7
+                rdy = torch.full((nshards,), epoch, dtype=torch.int32, device="cuda")
+                if ready_mask is not None:
+                    for q in range(nshards):
+                        if not (ready_mask >> q) & 1:
+                            rdy[q] = epoch - 1
+                fl5 = torch.full_like(flags, 9)
+                nf5 = torch.zeros(1, dtype=torch.int64, device="cuda")
+                hp.star_csr_fused(rp_l, col_l, row0, table, f_sh[s], None, nshards, rows, s, rdy, epoch, fl5, cws, nf5)
+                f5 = fl5.cpu().numpy()
+                fin = flags.cpu().numpy()
+                assert np.all((f5 == fin) | (f5 == 2)), (graph, nshards, ready_mask)
+                if ready_mask is None and graph == "hypercube":
+                    # <= 3 remote neighbours per row: everything inline but tiles with > 8 candidates
+                    assert np.count_nonzero(f5 == 2) <= np.count_nonzero(f4 == 2) // 50
+                if ready_mask == 0:
+                    assert np.array_equal(f5 == 2, f4 == 2)
+                assert int(nf5.item()) == int(nfev.item())
+                hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, fl5, None,
+                                   remote_at_ends=True, cand_ws=cws)
+                assert torch.equal(fl5, flags), (graph, nshards, ready_mask)
             got[row0:row0 + rows] = flags.cpu().numpy()
             assert int(nfev.item()) == int(np.count_nonzero(np.diff(rp_h[row0:row0 + rows + 1]) > 0))
         assert np.array_equal(got, ref), (graph, nshards)

@@ -1,6 +1,6 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU):
-pool / nfev of the sharded iteration with the p2p exchange == with the all_gather exchange == the
-single-GPU result computed by rank 0 on the whole problem.
+pool / nfev of the sharded iteration with the fused exchange == the two-phase p2p exchange == the
+all_gather exchange == the single-GPU result computed by rank 0 on the whole problem.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 tools/check_sharded.py [log2n]
@@ -29,9 +29,10 @@ rp_l = torch.arange(row0 * m, (row0 + rows + 1) * m, m, dtype=torch.int64, devic
 i = torch.arange(row0, row0 + rows, dtype=torch.int32, device=dev)[:, None]
 col_l = (i ^ (1 << torch.arange(m, dtype=torch.int32, device=dev))[None, :]).reshape(-1)
 res = {}
-for ex in ("p2p", "allgather", "p2p-walk"):
+for ex in ("fused", "p2p", "allgather", "p2p-walk"):
     it = sd.ShardedSobolIteration(F.F_RASTRIGIN, F.G_NONE, tab, n, rp_l, col_l, exchange=ex.split("-")[0],
-                                  remote_at_ends=(ex == "p2p"))
+                                  remote_at_ends=(ex in ("p2p", "fused")))
+    assert it.exchange == ex.split("-")[0]
     for _ in range(3):
         it.step()
     torch.cuda.synchronize()
@@ -39,6 +40,7 @@ for ex in ("p2p", "allgather", "p2p-walk"):
     it.close()
 ok = np.array_equal(res["p2p"][0], res["allgather"][0]) and res["p2p"][1] == res["allgather"][1]
 ok = ok and np.array_equal(res["p2p"][0], res["p2p-walk"][0])
+ok = ok and np.array_equal(res["p2p"][0], res["fused"][0]) and res["p2p"][1] == res["fused"][1]
 if rank == 0:
     rp, col = hp.hypercube_csr(n, dev)
     f, feas = hp.eval_sobol(F.F_RASTRIGIN, F.G_NONE, tab, 0, n)

@@ -30,12 +30,12 @@ for _ in range(K):
     hp.eval_sobol(it.functor, it.gset, it.tab, it.row0, it.rows, f=it.f_my, feasible=it.feas)
     ev[1].record()
     it._barrier_async()
-    hp.star_csr_local(it.row_ptr, it.col, it.row0, it.f_my, it.feas, it.is_min, it.nfev, it.off0, cand_ws=it._cand_ws[0], remote_at_ends=it.remote_at_ends)
+    hp.star_csr_local(it.row_ptr, it.col, it.row0, it.f_my, it.feas, it.is_min, it.nfev, it.off0, cand_ws=it._cand_ws, remote_at_ends=it.remote_at_ends)
     ev[2].record()
     it._barrier_wait()
     ev[3].record()
     hp.star_csr_remote(it.row_ptr, it.col, it.row0, it.peer.table, it.peer.own_ptr, it.world, it.rows, it.rank,
-                       it.is_min, it._remote_tmp, it.off0, remote_at_ends=True, cand_ws=it._cand_ws[0])
+                       it.is_min, it._remote_tmp, it.off0, remote_at_ends=True, cand_ws=it._cand_ws)
     ev[4].record()
     hp.compact_pool(it.is_min, base=it.row0, work=it.work)
     ev[5].record()
