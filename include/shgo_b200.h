@@ -121,6 +121,30 @@ SHGO_B200_API int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_
 SHGO_B200_API int shgo_b200_first_seen(const int32_t *simplices, uint64_t S, int dp1, uint64_t n,
                          uint64_t *first_seen, void *stream);
 
+/* ---- locality-preserving vertex numbering for explicit meshes -----------------
+ * qhull numbers a Delaunay mesh like the points it was handed, and Sobol order has no spatial
+ * locality: the star test's gathers of neighbour f values are then random 8-byte reads.  These calls
+ * build a Z-order (Morton) numbering of the vertices and move data between the two numberings; the
+ * classification is the same set of vertices either way (the reference has no counterpart: its
+ * vertices are Python objects in a dict, _vertex.py:304-317).
+ *   shgo_b200_morton_order  32-bit Z-order key per point (floor(32/d) bits per axis, first 32 axes)
+ *                           + stable radix sort: order[k] = old id at new position k, newid[old] = k
+ *                           (newid may be NULL).  x_soa: [d][ld] like shgo_b200_eval_points.
+ *   shgo_b200_relabel3      out [S][3] = newid[first three slots of every simplex] (dp1 == 2: the
+ *                           second slot twice; newid NULL: plain copy) -- exactly what vf_to_vv reads
+ *                           (_complex.py:1064-1069); feed it to shgo_b200_csr_from_simplices, dp1 = 3.
+ *   gather / scatter        dst[i] = src[idx[i]]  /  dst[idx[i]] = src[i]
+ */
+SHGO_B200_API size_t shgo_b200_morton_workspace(uint64_t n);
+SHGO_B200_API int shgo_b200_morton_order(const double *x_soa, uint64_t ld, int d, uint64_t n, const double *lb,
+                           const double *ub, int32_t *order, int32_t *newid, void *tmp,
+                           size_t tmp_bytes, void *stream);
+SHGO_B200_API int shgo_b200_relabel3(const int32_t *simplices, uint64_t S, int dp1, uint64_t n,
+                       const int32_t *newid, int32_t *out, void *stream);
+SHGO_B200_API int shgo_b200_gather_f64(const double *src, const int32_t *idx, uint64_t n, double *dst, void *stream);
+SHGO_B200_API int shgo_b200_gather_u8(const uint8_t *src, const int32_t *idx, uint64_t n, uint8_t *dst, void *stream);
+SHGO_B200_API int shgo_b200_scatter_u8(const uint8_t *src, const int32_t *idx, uint64_t n, uint8_t *dst, void *stream);
+
 /* ---- a6: star test ------------------------------------------------------------------------------------
  * Replaces VertexScalarField.minimiser / proc_minimisers (reference _vertex.py:144-151,
  * 422-426): is_min[r] = 1 iff row row0+r is non-empty and f[row0+r] < f[w] (strict) for every
@@ -225,9 +249,15 @@ SHGO_B200_API int shgo_b200_compact_pool(const uint8_t *is_min, uint64_t n, int6
 
 /* ---- a11: find_lowest_vertex (reference _shgo.py:863-880) ---------------------------------------
  * arg-min of f over vertices with present[i] != 0 (present may be NULL = all); ties resolve to the
- * lowest index; *idx = -1 and *val = +inf when nothing is finite.  tmp: 16 * 1024 bytes. */
+ * lowest index; *idx = -1 and *val = +inf when nothing is finite.  tmp: 32 * 1024 bytes.
+ * _ranked: ties resolve to the lowest rank[i] instead (rank = insertion order of the reference's
+ * vertex cache, e.g. shgo_b200_first_seen: the reference keeps the FIRST strictly lower vertex it
+ * meets in that order, so among equal values the earliest inserted one is its answer). */
 SHGO_B200_API int shgo_b200_argmin(const double *f, const uint8_t *present, uint64_t n, int64_t *idx,
                      double *val, void *tmp, size_t tmp_bytes, void *stream);
+SHGO_B200_API int shgo_b200_argmin_ranked(const double *f, const uint8_t *present, const int64_t *rank,
+                            uint64_t n, int64_t *idx, double *val, void *tmp, size_t tmp_bytes,
+                            void *stream);
 
 /* nfev bookkeeping (reference _vertex.py:184,347): number of vertices that exist (non-empty
  * row) and are feasible (feasible may be NULL). */

@@ -359,3 +359,22 @@ def lattice_star(d, gen, f):
     out = np.empty(nv, np.uint8)
     lib().oracle_lattice_star(d, gen, _p(f), _p(out))
     return out
+
+
+def morton_keys(x, bounds):
+    """32-bit Z-order key of every point (the numbering shgo_b200_morton_order sorts by; the
+    reference has no counterpart -- its vertices live in a dict, _vertex.py:304-317).  x: (n, d)."""
+    x = np.asarray(x, np.float64)
+    n, d = x.shape
+    b = np.asarray(bounds, np.float64).reshape(d, 2)
+    dk = min(d, 32)
+    bits = 30 if dk == 1 else 32 // dk
+    key = np.zeros(n, np.uint64)
+    for j in range(dk):
+        w = b[j, 1] - b[j, 0]
+        t = (x[:, j] - b[j, 0]) / w if w > 0 else np.zeros(n)
+        t = np.where(t == t, np.clip(t, 0.0, 1.0), 0.0)
+        q = np.minimum((t * float(1 << bits)).astype(np.uint64), np.uint64((1 << bits) - 1))
+        for bit in range(bits):
+            key |= ((q >> np.uint64(bit)) & np.uint64(1)) << np.uint64(bit * dk + (dk - 1 - j))
+    return key.astype(np.uint32)

@@ -23,6 +23,12 @@ SIGNATURES = {
     "shgo_b200_csr_workspace": (_sz, [_u64, _i, _u64]),
     "shgo_b200_csr_from_simplices": (_i, [_vp, _u64, _i, _u64, _vp, _vp, _u64, _vp, _vp, _sz, _vp]),
     "shgo_b200_first_seen": (_i, [_vp, _u64, _i, _u64, _vp, _vp]),
+    "shgo_b200_morton_workspace": (_sz, [_u64]),
+    "shgo_b200_morton_order": (_i, [_vp, _u64, _i, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "shgo_b200_relabel3": (_i, [_vp, _u64, _i, _u64, _vp, _vp, _vp]),
+    "shgo_b200_gather_f64": (_i, [_vp, _vp, _u64, _vp, _vp]),
+    "shgo_b200_gather_u8": (_i, [_vp, _vp, _u64, _vp, _vp]),
+    "shgo_b200_scatter_u8": (_i, [_vp, _vp, _u64, _vp, _vp]),
     "shgo_b200_star_csr": (_i, [_vp, _vp, _vp, _u64, _u64, _u64, _vp, _vp]),
     "shgo_b200_star_csr_nfev": (_i, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp]),
     "shgo_b200_star_csr_local": (_i, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _u64, _u64, _i, _vp, _vp, _sz, _vp,
@@ -40,6 +46,7 @@ SIGNATURES = {
     "shgo_b200_compact_workspace": (_sz, [_u64]),
     "shgo_b200_compact_pool": (_i, [_vp, _u64, _c.c_int64, _vp, _u64, _vp, _vp, _sz, _vp]),
     "shgo_b200_argmin": (_i, [_vp, _vp, _u64, _vp, _vp, _vp, _sz, _vp]),
+    "shgo_b200_argmin_ranked": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _sz, _vp]),
     "shgo_b200_count_nfev": (_i, [_vp, _vp, _u64, _vp, _vp]),
     "shgo_b200_lattice_eval": (_i, [_i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp]),
     "shgo_b200_lattice_eval_push": (_i, [_i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp, _i, _i, _i, ctypes.c_uint32, _vp]),

@@ -53,6 +53,10 @@ from . import lattice as lat
 
 
 _PENDING = threading.local()
+# meshes with at least this many vertices are ALSO kept in a Z-order (Morton) numbering of the points,
+# used by the star test only: qhull numbers the vertices like the (Sobol-ordered) points, so neighbour
+# ids are scattered over the whole range and the gathers of f miss every cache
+MORTON_MIN_VERTICES = 1 << 15
 LATTICE_MAX_DIM = 12     # closed-form star / local-bounds kernels (csrc/lattice.cu, bounds.cu); above: generator replay
 
 
@@ -302,6 +306,7 @@ class DeviceComplex:
         self._sampler = getattr(_PENDING, "sampler", None)   # consumed: one complex per driver call
         self._exact_cache_order = getattr(_PENDING, "exact_cache_order", False)
         _PENDING.sampler, _PENDING.exact_cache_order = None, False
+        self._morton = None          # mesh: (order, row_ptr, col) of the Z-order numbering, see vf_to_vv
         self._ref = None             # driver-side Python Complex used as a graph generator
         self._ref_keys = []
         self._lcb, self._lcb_key, self._x_soa = {}, None, None
@@ -390,6 +395,14 @@ class DeviceComplex:
         self._x_soa = None
         self._n = n
         self._dirty = True
+        self._morton = None
+        if n >= MORTON_MIN_VERTICES:
+            # the same graph in a locality-preserving numbering (acceleration structure of the star
+            # test; everything the driver sees stays in the mesh's own numbering)
+            self._x_soa = torch.from_numpy(pts).to(self.device).t().contiguous()
+            order, newid = hp.morton_order(self._x_soa, self.bounds)
+            rp_m, col_m = hp.csr_from_simplices(hp.relabel3(simp_d, n, newid), n)
+            self._morton = (order, rp_m, col_m)
 
     # =====================================================================================
     # evaluation + classification  (VertexCacheField.process_pools, _vertex.py:324-328)
@@ -460,8 +473,14 @@ class DeviceComplex:
             self._f, self._feas = self._evaluate_generic(x, None)
         else:
             self._f, self._feas = self._evaluate_generic(None, pts)
-        nf = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self._is_min = hp.star_csr(self._row_ptr, self._col, self._f, feasible=self._feas, nfev=nf)
+        if self.mode == "mesh" and self._morton is not None:
+            order, rp_m, col_m = self._morton
+            flags_m = hp.star_csr(rp_m, col_m, hp.gather(self._f, order))
+            self._is_min = hp.scatter_u8(flags_m, order, torch.empty(n, dtype=torch.uint8, device=self.device))
+            nf = hp.count_nfev(self._row_ptr, self._feas)
+        else:
+            nf = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._is_min = hp.star_csr(self._row_ptr, self._col, self._f, feasible=self._feas, nfev=nf)
         self.V.nfev = int(nf.item())
         present = (self._row_ptr[1:] > self._row_ptr[:-1]).to(torch.uint8)
         if self.mode == "hostgraph":
@@ -550,7 +569,10 @@ class DeviceComplex:
                 keys = self._stable_keys_of(pool)
                 pool = pool[np.array([k not in V._excluded for k in keys], bool)] if len(pool) else pool
         self.pool_indices = pool
-        self.argmin_index, self.argmin_value = hp.argmin(self._f, present)
+        # exact ties of f: the reference's find_lowest_vertex keeps the first strictly lower vertex in
+        # cache order (_shgo.py:863-880), i.e. the earliest inserted of the tied ones
+        self.argmin_index, self.argmin_value = hp.argmin(
+            self._f, present, self._rank if self.mode == "mesh" and self._rank is not None else None)
         V._reset_view()
         want = pool
         if self.argmin_index >= 0:

@@ -48,18 +48,15 @@ struct Replicas {
     int granule_log2;
 };
 
-template <class F, template <int> class SrcT, bool PUSH>
-__global__ void __launch_bounds__(kEvalThreads)
-eval_kernel(typename SrcT<F::P>::Params sp, int d, double *__restrict__ f,
-            uint8_t *__restrict__ feasible, const Replicas rep)
+// the persistent tile loop; `src` is a point source or a view of one (SobolSrc::View)
+template <class F, int TILE, bool PUSH, class Src>
+__device__ __forceinline__ void eval_tiles(Src &src, uint64_t ntiles, int d, double *__restrict__ f,
+                                           uint8_t *__restrict__ feasible, const Replicas &rep)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
     constexpr int P = F::P;
-    SrcT<P> src(sp, smem);
-    const uint64_t ntiles = src.num_tiles();
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         if (PUSH && rep.nparts > 1 &&
-            ((rep.id0 + tile * (uint64_t)SrcT<P>::kTile) >> rep.granule_log2) % rep.nparts != rep.part)
+            ((rep.id0 + tile * (uint64_t)TILE) >> rep.granule_log2) % rep.nparts != rep.part)
             continue;
         src.begin_tile(tile);
         double fv[P];
@@ -101,6 +98,28 @@ eval_kernel(typename SrcT<F::P>::Params sp, int d, double *__restrict__ f,
                 }
             }
         }
+    }
+}
+
+template <class F, template <int> class SrcT, bool PUSH>
+__global__ void __launch_bounds__(kEvalThreads)
+eval_kernel(typename SrcT<F::P>::Params sp, int d, double *__restrict__ f,
+            uint8_t *__restrict__ feasible, const Replicas rep)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int P = F::P;
+    SrcT<P> src(sp, smem);
+    const uint64_t ntiles = src.num_tiles();
+    if constexpr (SrcT<P>::kHasFastPath) {
+        if (src.fast_path()) {
+            typename SrcT<P>::template View<true> v{src};
+            eval_tiles<F, SrcT<P>::kTile, PUSH>(v, ntiles, d, f, feasible, rep);
+        } else {
+            typename SrcT<P>::template View<false> v{src};
+            eval_tiles<F, SrcT<P>::kTile, PUSH>(v, ntiles, d, f, feasible, rep);
+        }
+    } else {
+        eval_tiles<F, SrcT<P>::kTile, PUSH>(src, ntiles, d, f, feasible, rep);
     }
 }
 

@@ -267,21 +267,89 @@ __global__ void edge_fill_kernel(const unsigned long long *__restrict__ table, u
     }
 }
 
-// one warp per row: rank sort (entries of a row are distinct), col_tmp -> col
+// Rows are sorted ascending (entries of a row are distinct), col_tmp -> col, in two tiers:
+//   degree <= 32   one warp per row, rank by 32 shuffles (a Delaunay mesh in 2-D / 3-D is all of this)
+//   larger         listed, then one CTA per row: stable LSD radix sort, 8 bits per pass, ping-pong
+//                  between the row's slices of col_tmp and col -- O(deg) per pass instead of the
+//                  O(deg^2) rank sort of round 1 (a hub of 20 000 neighbours: 4e8 comparisons on 32 lanes)
 __global__ void __launch_bounds__(256)
-row_sort_kernel(const int64_t *__restrict__ row_ptr, uint64_t n, const int32_t *__restrict__ col_tmp,
-                int32_t *__restrict__ col)
+row_sort_small_kernel(const int64_t *__restrict__ row_ptr, uint64_t n, const int32_t *__restrict__ col_tmp,
+                      int32_t *__restrict__ col, uint32_t *__restrict__ big_list, int *__restrict__ big_count)
 {
     const int lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
         const int64_t b = row_ptr[r], e = row_ptr[r + 1];
-        for (int64_t i = b + lane; i < e; i += 32) {
-            const int32_t v = col_tmp[i];
-            int64_t rank = 0;
-            for (int64_t k = b; k < e; ++k) rank += col_tmp[k] < v;
-            col[b + rank] = v;
+        const int64_t len = e - b;
+        if (len == 0) continue;
+        if (len > 32) {
+            if (lane == 0) big_list[atomicAdd(big_count, 1)] = (uint32_t)r;
+            continue;
         }
+        const int32_t v = lane < len ? col_tmp[b + lane] : 0x7fffffff;
+        int rank = 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) rank += __shfl_sync(0xffffffffu, v, k) < v;
+        if (lane < len) col[b + rank] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+row_sort_big_kernel(const int64_t *__restrict__ row_ptr, int32_t *__restrict__ col_tmp, int32_t *__restrict__ col,
+                    const uint32_t *__restrict__ big_list, const int *__restrict__ big_count, int npass)
+{
+    __shared__ uint32_t hist[256], base[256], running[256];
+    __shared__ uint32_t cnt[kScanThreads / 32][256];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int nbig = *big_count;
+    for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
+        const uint32_t r = big_list[q];
+        const int64_t b = row_ptr[r];
+        const uint32_t len = (uint32_t)(row_ptr[r + 1] - b);
+        uint32_t *A = reinterpret_cast<uint32_t *>(col_tmp + b), *B = reinterpret_cast<uint32_t *>(col + b);
+        for (int p = 0; p < npass; ++p) {
+            const uint32_t *in = (p & 1) ? B : A;
+            uint32_t *out = (p & 1) ? A : B;
+            const int shift = 8 * p;
+            hist[t] = 0;
+            __syncthreads();
+            for (uint32_t i = t; i < len; i += kScanThreads) atomicAdd(&hist[(in[i] >> shift) & 0xffu], 1u);
+            __syncthreads();
+            uint32_t total;
+            const uint32_t ex = block_exclusive_scan(hist[t], &total);
+            base[t] = ex;
+            running[t] = 0;
+#pragma unroll
+            for (int k = 0; k < kScanThreads / 32; ++k) cnt[k][t] = 0;
+            __syncthreads();
+            for (uint32_t r0 = 0; r0 < len; r0 += kScanThreads) {
+                const uint32_t i = r0 + t;
+                const bool live = i < len;
+                const uint32_t key = live ? in[i] : 0u;
+                const uint32_t dg = live ? ((key >> shift) & 0xffu) : 0x100u;
+                const unsigned peers = __match_any_sync(0xffffffffu, dg);
+                const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+                if (live && below == 0) cnt[w][dg] = __popc(peers);
+                __syncthreads();
+                if (live) {
+                    uint32_t off = base[dg] + running[dg] + below;
+                    for (int k = 0; k < w; ++k) off += cnt[k][dg];
+                    out[off] = key;
+                }
+                __syncthreads();
+                uint32_t sum = 0;
+#pragma unroll
+                for (int k = 0; k < kScanThreads / 32; ++k) {
+                    sum += cnt[k][t];
+                    cnt[k][t] = 0;
+                }
+                running[t] += sum;
+                __syncthreads();
+            }
+        }
+        if ((npass & 1) == 0)  // an even number of passes ends in col_tmp
+            for (uint32_t i = t; i < len; i += kScanThreads) B[i] = A[i];
+        __syncthreads();
     }
 }
 
@@ -290,33 +358,37 @@ row_sort_kernel(const int64_t *__restrict__ row_ptr, uint64_t n, const int32_t *
 // =============================================================================================
 struct MinPair {
     double v;
-    int64_t i;
+    int64_t i;  // vertex index, -1 = none
+    int64_t k;  // tie-break key: the caller's rank of the vertex, else its index
 };
 __device__ __forceinline__ MinPair min_pair(MinPair a, MinPair b)
 {
-    if (b.i >= 0 && (a.i < 0 || b.v < a.v || (b.v == a.v && b.i < a.i))) return b;
+    if (b.i >= 0 && (a.i < 0 || b.v < a.v || (b.v == a.v && b.k < a.k))) return b;
     return a;
 }
 __device__ __forceinline__ MinPair block_min(MinPair m)
 {
     __shared__ double sv[32];
-    __shared__ long long si[32];
+    __shared__ long long si[32], sk[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        MinPair y{__shfl_down_sync(0xffffffffu, m.v, o), __shfl_down_sync(0xffffffffu, m.i, o)};
+        MinPair y{__shfl_down_sync(0xffffffffu, m.v, o), __shfl_down_sync(0xffffffffu, m.i, o),
+                  __shfl_down_sync(0xffffffffu, m.k, o)};
         m = min_pair(m, y);
     }
     if (lane == 0) {
         sv[w] = m.v;
         si[w] = m.i;
+        sk[w] = m.k;
     }
     __syncthreads();
     if (w == 0) {
-        m = lane < nw ? MinPair{sv[lane], si[lane]} : MinPair{pos_inf(), -1};
+        m = lane < nw ? MinPair{sv[lane], si[lane], sk[lane]} : MinPair{pos_inf(), -1, 0};
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            MinPair y{__shfl_down_sync(0xffffffffu, m.v, o), __shfl_down_sync(0xffffffffu, m.i, o)};
+            MinPair y{__shfl_down_sync(0xffffffffu, m.v, o), __shfl_down_sync(0xffffffffu, m.i, o),
+                      __shfl_down_sync(0xffffffffu, m.k, o)};
             m = min_pair(m, y);
         }
     }
@@ -324,17 +396,22 @@ __device__ __forceinline__ MinPair block_min(MinPair m)
 }
 
 __global__ void __launch_bounds__(256)
-argmin_partial_kernel(const double *__restrict__ f, const uint8_t *__restrict__ present, uint64_t n,
-                      MinPair *__restrict__ partial)
+argmin_partial_kernel(const double *__restrict__ f, const uint8_t *__restrict__ present,
+                      const int64_t *__restrict__ rank, uint64_t n, MinPair *__restrict__ partial)
 {
-    MinPair m{pos_inf(), -1};
+    MinPair m{pos_inf(), -1, 0};
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
         if (present && !present[i]) continue;
-        double v = ld_nc_f64(f + i);
-        if (v < m.v) {  // strict: +inf never wins, first (lowest) index wins ties
+        const double v = ld_nc_f64(f + i);
+        if (!(v < pos_inf())) continue;  // +inf and NaN never win
+        const int64_t k = rank ? rank[i] : (int64_t)i;
+        // ties: the lowest key wins (the reference keeps the first strictly lower vertex in cache
+        // order, _shgo.py:863-880: among equal values that is the earliest inserted one)
+        if (m.i < 0 || v < m.v || (v == m.v && k < m.k)) {
             m.v = v;
             m.i = (int64_t)i;
+            m.k = k;
         }
     }
     m = block_min(m);
@@ -344,7 +421,7 @@ argmin_partial_kernel(const double *__restrict__ f, const uint8_t *__restrict__ 
 __global__ void __launch_bounds__(1024)
 argmin_final_kernel(const MinPair *__restrict__ partial, int nparts, int64_t *idx, double *val)
 {
-    MinPair m{pos_inf(), -1};
+    MinPair m{pos_inf(), -1, 0};
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) m = min_pair(m, partial[i]);
     m = block_min(m);
     if (threadIdx.x == 0) {
@@ -502,7 +579,7 @@ int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, 
 
     SHGO_CUDA_TRY(cudaMemsetAsync(table, 0xff, slots * 8, st));
     SHGO_CUDA_TRY(cudaMemsetAsync(deg, 0, align256(n * 4) * 2, st));  // deg + cursor
-    SHGO_CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    SHGO_CUDA_TRY(cudaMemsetAsync(bad, 0, 2 * sizeof(int), st));  // bad flag, number of long rows
     if (S > 0)
         edge_insert_kernel<<<grid_for(S, 256, 8), 256, 0, st>>>(simplices, S, dp1, n, table, slots - 1,
                                                                 deg, bad);
@@ -512,7 +589,12 @@ int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, 
     rowptr_kernel<<<(unsigned)(n / kScanBlock + 1), kScanThreads, 0, st>>>(deg, n, sums, row_ptr);
     if (S > 0) {
         edge_fill_kernel<<<grid_for(slots, 256, 8), 256, 0, st>>>(table, slots, row_ptr, cursor, col_tmp);
-        row_sort_kernel<<<grid_for(n * 32, 256, 8), 256, 0, st>>>(row_ptr, n, col_tmp, col);
+        // `cursor` is free after the fill: it takes the list of rows longer than a warp
+        row_sort_small_kernel<<<grid_for(n * 32, 256, 8), 256, 0, st>>>(row_ptr, n, col_tmp, col, cursor, bad + 1);
+        int npass = 1;
+        while (npass < 4 && (n - 1) >> (8 * npass)) ++npass;  // vertex ids < n: skip all-zero digits
+        row_sort_big_kernel<<<(unsigned)sm_count() * 4, kScanThreads, 0, st>>>(row_ptr, col_tmp, col, cursor, bad + 1,
+                                                                             npass);
         flag_bad_kernel<<<1, 1, 0, st>>>(bad, nnz);
     }
     SHGO_CUDA_TRY(cudaGetLastError());
@@ -537,6 +619,12 @@ int shgo_b200_first_seen(const int32_t *simplices, uint64_t S, int dp1, uint64_t
 int shgo_b200_argmin(const double *f, const uint8_t *present, uint64_t n, int64_t *idx, double *val,
                      void *tmp, size_t tmp_bytes, void *stream)
 {
+    return shgo_b200_argmin_ranked(f, present, nullptr, n, idx, val, tmp, tmp_bytes, stream);
+}
+
+int shgo_b200_argmin_ranked(const double *f, const uint8_t *present, const int64_t *rank, uint64_t n,
+                            int64_t *idx, double *val, void *tmp, size_t tmp_bytes, void *stream)
+{
     SHGO_REQUIRE(idx && val && tmp, "null pointer");
     SHGO_REQUIRE(f || n == 0, "null f");
     SHGO_REQUIRE(tmp_bytes >= 1024 * sizeof(MinPair), "argmin workspace: need %zu bytes",
@@ -545,7 +633,7 @@ int shgo_b200_argmin(const double *f, const uint8_t *present, uint64_t n, int64_
     unsigned blocks = grid_for(n ? n : 1, 256, 4);
     if (blocks > 1024) blocks = 1024;
     MinPair *partial = static_cast<MinPair *>(tmp);
-    argmin_partial_kernel<<<blocks, 256, 0, st>>>(f, present, n, partial);
+    argmin_partial_kernel<<<blocks, 256, 0, st>>>(f, present, rank, n, partial);
     argmin_final_kernel<<<1, 1024, 0, st>>>(partial, (int)blocks, idx, val);
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;

@@ -156,6 +156,47 @@ def csr_from_simplices(simplices, n):
     return row_ptr, col[:count]
 
 
+def morton_order(x_soa, bounds):
+    """Z-order numbering of the points x_soa = (d, n): (order, newid) int32 tensors with
+    order[new] = old and newid[old] = new."""
+    d, n = x_soa.shape
+    dev = x_soa.device
+    lb, ub = _bounds_vectors(bounds, d, dev)
+    order = torch.empty(n, dtype=torch.int32, device=dev)
+    newid = torch.empty(n, dtype=torch.int32, device=dev)
+    ws = _lib.lib().shgo_b200_morton_workspace(n)
+    tmp = torch.empty(ws, dtype=torch.uint8, device=dev)
+    _lib.call("shgo_b200_morton_order", _ptr(x_soa), soa_ld(x_soa), d, n, _ptr(lb), _ptr(ub), _ptr(order),
+              _ptr(newid), _ptr(tmp), ws, _stream())
+    return order, newid
+
+
+def relabel3(simplices, n, newid=None):
+    """(S, 3) int32: the first three slots of every simplex (all that vf_to_vv reads), renumbered."""
+    assert simplices.dtype == torch.int32 and simplices.dim() == 2
+    simplices = simplices.contiguous()
+    S, dp1 = simplices.shape
+    out = torch.empty((S, 3), dtype=torch.int32, device=simplices.device)
+    _lib.call("shgo_b200_relabel3", _ptr(simplices), S, dp1, n, _ptr(newid), _ptr(out), _stream())
+    return out
+
+
+def gather(src, idx, out=None):
+    """out[i] = src[idx[i]] (float64 or uint8 src, int32 idx)"""
+    n = idx.numel()
+    if out is None:
+        out = torch.empty(n, dtype=src.dtype, device=src.device)
+    name = {torch.float64: "shgo_b200_gather_f64", torch.uint8: "shgo_b200_gather_u8"}[src.dtype]
+    _lib.call(name, _ptr(src), _ptr(idx), n, _ptr(out), _stream())
+    return out
+
+
+def scatter_u8(src, idx, out):
+    """out[idx[i]] = src[i]"""
+    _lib.call("shgo_b200_scatter_u8", _ptr(src), _ptr(idx), idx.numel(), _ptr(out), _stream())
+    return out
+
+
 def first_seen(simplices, n):
     """int64 [n]: position at which vf_to_vv first touches each vertex (-1 = never)."""
     assert simplices.dtype == torch.int32 and simplices.dim() == 2
@@ -281,13 +322,15 @@ def compact_pool(is_min, base=0, cap=None, work=None):
     return work.idx, work.count[0]
 
 
-def argmin(f, present=None):
+def argmin(f, present=None, rank=None):
+    """(index, value) of the lowest finite f among the present vertices; ties go to the lowest
+    rank (int64 per vertex: the reference's cache order) when given, else to the lowest index."""
     dev = f.device
     idx = torch.empty(1, dtype=torch.int64, device=dev)
     val = torch.empty(1, dtype=torch.float64, device=dev)
-    tmp = torch.empty(16 * 1024, dtype=torch.uint8, device=dev)
-    _lib.call("shgo_b200_argmin", _ptr(f), _ptr(present), f.numel(), _ptr(idx), _ptr(val), _ptr(tmp),
-              tmp.numel(), _stream())
+    tmp = torch.empty(32 * 1024, dtype=torch.uint8, device=dev)
+    _lib.call("shgo_b200_argmin_ranked", _ptr(f), _ptr(present), _ptr(rank), f.numel(), _ptr(idx), _ptr(val),
+              _ptr(tmp), tmp.numel(), _stream())
     return int(idx.item()), float(val.item())
 
 

@@ -79,6 +79,31 @@ def shgo_b200_first_seen(simplices, S, dp1, n, first_seen, stream):
     _req(dp1 >= 2, "simplices need at least two vertex slots (dp1 = %d)", dp1)
 
 
+def shgo_b200_morton_order(x_soa, ld, d, n, lb, ub, order, newid, tmp, tmp_bytes, stream):
+    _req(d >= 1, "d must be positive (got %d)", d)
+    _req(n <= 0x7fffffff, "vertex count out of int32 range")
+    if n == 0:
+        return
+    _req(x_soa and lb and ub and order and tmp, "null pointer")
+    _req(ld >= n, "ld < n")
+
+
+def shgo_b200_relabel3(simplices, S, dp1, n, newid, out, stream):
+    _req(dp1 >= 2, "simplices need at least two vertex slots (dp1 = %d)", dp1)
+    if S == 0:
+        return
+    _req(simplices and out, "null pointer")
+
+
+def _gs(src, idx, n, dst, stream):
+    if n == 0:
+        return
+    _req(src and idx and dst, "null pointer")
+
+
+shgo_b200_gather_f64 = shgo_b200_gather_u8 = shgo_b200_scatter_u8 = _gs
+
+
 def shgo_b200_star_csr(row_ptr, col, f, row0, rows, nnz_hint, is_min, stream):
     if rows == 0:
         return
@@ -125,10 +150,14 @@ def shgo_b200_compact_pool(is_min, n, base, idx_out, cap, count, tmp, tmp_bytes,
     _req(idx_out or cap == 0, "null idx_out with cap > 0")
 
 
-def shgo_b200_argmin(f, present, n, idx, val, tmp, tmp_bytes, stream):
+def shgo_b200_argmin_ranked(f, present, rank, n, idx, val, tmp, tmp_bytes, stream):
     _req(idx and val and tmp, "null pointer")
     _req(f or n == 0, "null f")
-    _req(tmp_bytes >= 1024 * 16, "argmin workspace: need %d bytes", 1024 * 16)
+    _req(tmp_bytes >= 1024 * 24, "argmin workspace: need %d bytes", 1024 * 24)
+
+
+def shgo_b200_argmin(f, present, n, idx, val, tmp, tmp_bytes, stream):
+    shgo_b200_argmin_ranked(f, present, None, n, idx, val, tmp, tmp_bytes, stream)
 
 
 def shgo_b200_count_nfev(row_ptr, feasible, n, count, stream):

@@ -61,6 +61,37 @@ def csr_from_simplices(simplices, n):
     return torch.from_numpy(rp), torch.from_numpy(col)
 
 
+def morton_order(x_soa, bounds):
+    """any locality-ish permutation serves the host logic: stable sort by a coarse Z-order key"""
+    key = orc.morton_keys(np.ascontiguousarray(x_soa.numpy().T), np.asarray(bounds, float))
+    order = np.argsort(key, kind="stable").astype(np.int32)
+    newid = np.empty_like(order)
+    newid[order] = np.arange(len(order), dtype=np.int32)
+    return torch.from_numpy(order), torch.from_numpy(newid)
+
+
+def relabel3(simplices, n, newid=None):
+    s = simplices.numpy()
+    s3 = s[:, :3] if s.shape[1] >= 3 else np.concatenate([s, s[:, 1:2]], 1)
+    if newid is not None:
+        s3 = newid.numpy()[s3]
+    return torch.from_numpy(np.ascontiguousarray(s3.astype(np.int32)))
+
+
+def gather(src, idx, out=None):
+    return src[idx.to(torch.int64)].contiguous()
+
+
+def scatter_u8(src, idx, out):
+    out[idx.to(torch.int64)] = src
+    return out
+
+
+def count_nfev(row_ptr, feasible=None, out=None):
+    c = orc.nfev(row_ptr.numpy(), None if feasible is None else feasible.numpy())
+    return torch.tensor([int(c)], dtype=torch.int64)
+
+
 def first_seen(simplices, n):
     s = simplices.numpy()
     k = min(s.shape[1], 3)
@@ -117,9 +148,15 @@ def _compact_pool(is_min, base=0):
     return torch.from_numpy(idx), torch.tensor(len(idx))
 
 
-def argmin(f, present=None):
+def argmin(f, present=None, rank=None):
     fh = f.numpy()
     i = orc.argmin(fh, None if present is None else np.ascontiguousarray(present.numpy()))
+    if i >= 0 and rank is not None:       # ties: the lowest rank instead of the lowest index
+        tie = fh == fh[i]
+        if present is not None:
+            tie &= present.numpy() != 0
+        cand = np.flatnonzero(tie)
+        i = int(cand[np.argmin(rank.numpy()[cand])])
     return i, (float(fh[i]) if i >= 0 else float("inf"))
 
 
@@ -234,7 +271,7 @@ def install(monkeypatch):
     """Patch shgo_b200.hotpath in place (functions are looked up as attributes at call time)."""
     from shgo_b200 import hotpath as hp
     for name in ("SobolTables", "sobol_points", "eval_sobol", "eval_points", "mask_infeasible",
-                 "csr_from_simplices", "first_seen", "star_csr", "star_csr_shard", "PoolWorkspace", "compact_pool", "argmin", "lattice_eval",
+                 "csr_from_simplices", "count_nfev", "morton_order", "relabel3", "gather", "scatter_u8", "first_seen", "star_csr", "star_csr_shard", "PoolWorkspace", "compact_pool", "argmin", "lattice_eval",
                  "lattice_coords", "lattice_star", "local_bounds_csr", "lattice_local_bounds", "lattice_eval_push"):
         obj = globals()[name]
         real = getattr(hp, name)

@@ -693,3 +693,80 @@ def test_lattice_granule_cyclic_parts_emulated_on_one_gpu(hp, nparts):
         union += fl
     assert torch.equal(union, ref)
     assert np.array_equal(ref.cpu().numpy(), orc.lattice_star(d, gen, f_ref.cpu().numpy()))
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,n", [(1, 1000), (2, 70001), (3, 4096), (6, 20000), (8, 5000), (40, 3000)])
+def test_morton_order_is_a_stable_sort_by_the_z_order_key(hp, d, n):
+    rng = np.random.default_rng(d)
+    bounds = np.stack([rng.uniform(-5, 0, d), rng.uniform(1, 9, d)], 1)
+    pts = rng.uniform(bounds[:, 0], bounds[:, 1], size=(n, d))
+    pts[::97] = pts[1]                                # coincident points: ties keep index order
+    pts[5] = bounds[:, 1]                             # a point on the upper faces
+    x = torch.from_numpy(pts).cuda().t().contiguous()
+    order, newid = hp.morton_order(x, bounds)
+    order, newid = order.cpu().numpy(), newid.cpu().numpy()
+    key = orc.morton_keys(pts, bounds)
+    assert np.array_equal(order, np.argsort(key, kind="stable"))
+    assert np.array_equal(newid[order], np.arange(n))
+
+
+def test_star_test_in_morton_numbering_gives_the_same_pool(hp):
+    """real qhull meshes (2-D and 3-D Sobol points): CSR in the mesh's own numbering vs in Z-order,
+    pools identical after mapping back, and identical to the oracle's"""
+    from scipy.spatial import Delaunay
+    for d, n in ((2, 1 << 14), (3, 1 << 12)):
+        bounds = [(-5.12, 5.12)] * d
+        tab = hp.SobolTables(bounds)
+        pts = hp.sobol_points(tab, 0, n, "aos").cpu().numpy()
+        simp = Delaunay(pts).simplices.astype(np.int32)
+        simp_d = torch.from_numpy(simp).cuda()
+        f, _ = hp.eval_sobol(orc.FUNCTOR_IDS["rastrigin"], 0, tab, 0, n)
+        rp, col = hp.csr_from_simplices(simp_d, n)
+        flags = hp.star_csr(rp, col, f)
+        x = hp.sobol_points(tab, 0, n, "soa")
+        order, newid = hp.morton_order(x, bounds)
+        s3 = hp.relabel3(simp_d, n, newid)
+        assert np.array_equal(s3.cpu().numpy(), newid.cpu().numpy()[simp[:, :3]])
+        rp_m, col_m = hp.csr_from_simplices(s3, n)
+        assert int(rp_m[-1]) == int(rp[-1])
+        flags_m = hp.star_csr(rp_m, col_m, hp.gather(f, order))
+        back = hp.scatter_u8(flags_m, order, torch.empty(n, dtype=torch.uint8, device="cuda"))
+        assert torch.equal(back, flags)
+        rp_o, col_o = orc.vf_to_vv(simp, n)
+        assert np.array_equal(back.cpu().numpy(), orc.star_csr(rp_o, col_o, f.cpu().numpy()))
+        # locality: mean |row - neighbour| drops by an order of magnitude
+        def spread(rpt, ct):
+            rows = np.repeat(np.arange(n), np.diff(rpt.cpu().numpy()))
+            return np.abs(rows - ct.cpu().numpy()).mean()
+        assert spread(rp_m, col_m) * 8 < spread(rp, col)
+
+
+def test_csr_rows_longer_than_a_warp_are_sorted(hp):
+    """hubs: rows of 33 ... 50 000 entries go through the per-row radix sort"""
+    rng = np.random.default_rng(3)
+    n = 60000
+    hubs = [0, 17, 40000]
+    sizes = [33, 700, 50000]
+    tri = []
+    for h, m in zip(hubs, sizes):
+        others = rng.choice(np.setdiff1d(np.arange(n), hubs), m, replace=False)
+        tri.append(np.stack([np.full(m, h), others, np.roll(others, 1)], 1))
+    tri.append(rng.integers(0, n, size=(30000, 3)))
+    simp = np.concatenate(tri).astype(np.int32)
+    rp, col = hp.csr_from_simplices(torch.from_numpy(simp).cuda(), n)
+    rp_o, col_o = orc.vf_to_vv(simp, n)
+    assert np.array_equal(rp.cpu().numpy(), rp_o) and np.array_equal(col.cpu().numpy(), col_o)
+
+
+def test_argmin_breaks_ties_by_rank(hp):
+    f = torch.tensor([3.0, 1.0, float("inf"), 1.0, 2.0, 1.0, float("nan")], dtype=torch.float64, device="cuda")
+    assert hp.argmin(f) == (1, 1.0)
+    rank = torch.tensor([5, 9, 0, 7, 1, 2, 3], dtype=torch.int64, device="cuda")
+    assert hp.argmin(f, None, rank) == (5, 1.0)
+    present = torch.tensor([1, 1, 1, 1, 1, 0, 1], dtype=torch.uint8, device="cuda")
+    assert hp.argmin(f, present, rank) == (3, 1.0)
+    big = torch.full((1 << 20,), 2.5, dtype=torch.float64, device="cuda")
+    r = torch.arange(1 << 20, 0, -1, dtype=torch.int64, device="cuda")
+    assert hp.argmin(big, None, r)[0] == (1 << 20) - 1 and hp.argmin(big)[0] == 0
+    assert hp.argmin(torch.full((10,), float("inf"), dtype=torch.float64, device="cuda")) == (-1, float("inf"))

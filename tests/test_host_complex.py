@@ -240,3 +240,20 @@ def test_shgo_object_does_not_leave_the_driver_patched(sb):
     s.iterate_all()
     r.iterate_all()
     assert s.res.nfev == r.res.nfev and np.allclose(s.res.x, r.res.x)
+
+
+def test_mesh_classified_in_morton_numbering_gives_the_same_result(sb, monkeypatch):
+    """Large meshes are also kept in a Z-order numbering for the star test (complex.MORTON_MIN_VERTICES):
+    the driver must not see any difference -- same result object with the threshold forced to 0."""
+    from shgo_b200 import complex as cx, functors as F
+    kw = dict(n=128, iters=2, sampling_method="sobol")
+    bounds = [(-5.12, 5.12)] * 3
+    plain = sb.shgo(F.rastrigin, bounds, **kw)
+    monkeypatch.setattr(cx, "MORTON_MIN_VERTICES", 0)
+    used = []
+    real = cx.hp.morton_order
+    monkeypatch.setattr(cx.hp, "morton_order", lambda *a, **k: used.append(1) or real(*a, **k))
+    morton = sb.shgo(F.rastrigin, bounds, **kw)
+    assert used, "the Z-order numbering was not exercised"
+    assert (plain.nfev, plain.nit, plain.nlfev) == (morton.nfev, morton.nit, morton.nlfev)
+    assert np.array_equal(plain.xl, morton.xl) and np.array_equal(plain.funl, morton.funl)
