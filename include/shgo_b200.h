@@ -247,6 +247,30 @@ SHGO_B200_API int shgo_b200_compact_pool(const uint8_t *is_min, uint64_t n, int6
                            uint64_t cap, uint64_t *count, void *tmp, size_t tmp_bytes,
                            void *stream);
 
+/* ---- a4': SHGO.sampling_subspace (reference _shgo.py:1452-1463) --------------------------------------
+ * With options['infty_constraints'] = False the driver drops the sample points that violate a
+ * constraint BEFORE triangulating: C = C[g(C.T) >= 0.0] for every g.  keep[i] = 1 iff every
+ * g[c][i] >= 0.0 (g: [m][n], e.g. the constraint callables evaluated on the device tensor); a NaN
+ * drops the point -- the opposite of feasibility_check's rule (shgo_b200_mask_infeasible).  The kept
+ * row indices come from shgo_b200_compact_pool(keep), the surviving points in the driver's C-order
+ * (m, d) layout from shgo_b200_gather_rows (out[r][j] = x_soa[j][idx[r]]). */
+SHGO_B200_API int shgo_b200_subspace_mask(const double *g, int m, uint64_t n, uint8_t *keep, void *stream);
+SHGO_B200_API int shgo_b200_gather_rows(const double *x_soa, uint64_t ld, int d, const int64_t *idx, uint64_t m,
+                          double *out, void *stream);
+
+/* ---- f3: pool post-processing (reference _shgo.py:1116-1122, 1213-1219, 1227-1243) ------------------
+ * SHGO.minimizers skips pool vertices whose coordinates equal an earlier local minimum (LMC.xl_maps),
+ * sort_min_pool orders the pool by f, g_topograph by distance from a point.  pool: m vertex ids in the
+ * reference's cache order; xl: [k][d] coordinates to exclude (k may be 0).  ranked receives the
+ * remaining ids ordered by mode 0: f[id] ascending, mode 1: euclidean distance from xref[d] ascending
+ * (sum of squares accumulated axis by axis, then sqrt, like scipy's cdist); equal keys keep the
+ * pool's order (the reference's np.argsort does not promise an order among equal keys).  *count =
+ * number of ids written.  tmp: shgo_b200_pool_rank_workspace(m) bytes. */
+SHGO_B200_API size_t shgo_b200_pool_rank_workspace(uint64_t m);
+SHGO_B200_API int shgo_b200_pool_rank(const int64_t *pool, uint64_t m, const double *f, const double *x_soa,
+                        uint64_t ld, int d, const double *xl, int k, int mode, const double *xref,
+                        int64_t *ranked, uint64_t *count, void *tmp, size_t tmp_bytes, void *stream);
+
 /* ---- a11: find_lowest_vertex (reference _shgo.py:863-880) ---------------------------------------
  * arg-min of f over vertices with present[i] != 0 (present may be NULL = all); ties resolve to the
  * lowest index; *idx = -1 and *val = +inf when nothing is finite.  tmp: 32 * 1024 bytes.

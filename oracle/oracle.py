@@ -378,3 +378,28 @@ def morton_keys(x, bounds):
         for bit in range(bits):
             key |= ((q >> np.uint64(bit)) & np.uint64(1)) << np.uint64(bit * dk + (dk - 1 - j))
     return key.astype(np.uint32)
+
+
+def sampling_subspace(C, g_funcs):
+    """restatement of SHGO.sampling_subspace, reference _shgo.py:1452-1463 (C: (n, d) points)"""
+    idx = np.arange(C.shape[0])
+    for g in g_funcs:
+        keep = g(C.T) >= 0.0
+        C, idx = C[keep], idx[keep]
+    return idx, C
+
+
+def pool_rank(pool, f, x=None, xl=(), by="f", xref=None):
+    """restatement of the pool post-processing of SHGO.minimizers / sort_min_pool / g_topograph
+    (reference _shgo.py:1116-1122, 1213-1219, 1227-1243) with a STABLE argsort"""
+    pool = np.asarray(pool, np.int64)
+    keep = np.ones(len(pool), bool)
+    for xm in xl:
+        keep &= ~np.all(x[pool] == np.asarray(xm), axis=1)
+    pool = pool[keep]
+    if by == "f":
+        key = f[pool]
+    else:
+        from scipy import spatial
+        key = spatial.distance.cdist(np.array([xref]), x[pool], "euclidean")[0]
+    return pool[np.argsort(key, kind="stable")]

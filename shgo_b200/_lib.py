@@ -46,6 +46,10 @@ SIGNATURES = {
     "shgo_b200_compact_workspace": (_sz, [_u64]),
     "shgo_b200_compact_pool": (_i, [_vp, _u64, _c.c_int64, _vp, _u64, _vp, _vp, _sz, _vp]),
     "shgo_b200_argmin": (_i, [_vp, _vp, _u64, _vp, _vp, _vp, _sz, _vp]),
+    "shgo_b200_subspace_mask": (_i, [_vp, _i, _u64, _vp, _vp]),
+    "shgo_b200_gather_rows": (_i, [_vp, _u64, _i, _vp, _u64, _vp, _vp]),
+    "shgo_b200_pool_rank_workspace": (_sz, [_u64]),
+    "shgo_b200_pool_rank": (_i, [_vp, _u64, _vp, _vp, _u64, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "shgo_b200_argmin_ranked": (_i, [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _sz, _vp]),
     "shgo_b200_count_nfev": (_i, [_vp, _vp, _u64, _vp, _vp]),
     "shgo_b200_lattice_eval": (_i, [_i, _i, _i, _i, _vp, _u64, _u64, _vp, _vp, _vp]),

@@ -59,6 +59,62 @@ def _device_lcb(saved):
     return construct_lcb_simplicial
 
 
+# pools of at least this many vertices are filtered / ranked on the device; below,
+# the driver's own loop over the handful of materialised vertices is used unchanged
+DEVICE_POOL_RANK_MIN = 2048
+
+
+def _device_minimizers(saved):
+    """SHGO.minimizers (_shgo.py:1109-1157) with the LMC exclusion and the f-ordering done on the
+    device for large pools; produces the same attributes as the driver's loop + sort_min_pool.  Among
+    exactly equal f values the order is the cache order (np.argsort promises none)."""
+    def minimizers(self):
+        HC = self.HC
+        if not (isinstance(HC, _cx.DeviceComplex) and len(HC._pool_cache_order) >= DEVICE_POOL_RANK_MIN):
+            return saved(self)
+        xl = list(self.LMC.xl_maps) if len(self.LMC.xl_maps) > 0 else []
+        ranked = HC.ranked_pool(xl)
+        kept = set(ranked.tolist())
+        by_index = HC.V._by_index
+        in_cache_order = [by_index[i] for i in HC._pool_cache_order.tolist() if i in kept]
+        self.X_min = np.array([v.x_a for v in in_cache_order])
+        self.X_min_cache = {tuple(v.x_a): v.x for v in in_cache_order}
+        pool = np.empty(len(ranked), dtype=object)
+        pool[:] = [by_index[i] for i in ranked.tolist()]
+        self.minimizer_pool = pool
+        self.minimizer_pool_F = np.array([v.f for v in pool], dtype=float)
+        return self.X_min
+
+    minimizers.__doc__ = saved.__doc__
+    return minimizers
+
+
+def _device_subspace(saved):
+    """SHGO.sampling_subspace (_shgo.py:1452-1463) on the device when the constraints allow it"""
+    def sampling_subspace(self):
+        C = None
+        if isinstance(getattr(self, "HC", None), _cx.DeviceComplex):
+            C = _cx.device_sampling_subspace(self.C, self.g_cons, self.g_args)
+        if C is None:
+            return saved(self)
+        self.C = C
+        if self.C.size == 0:
+            self.res.message = ('No sampling point found within the '
+                                + 'feasible set. Increasing sampling '
+                                + 'size.')
+            if self.disp:
+                import logging
+                logging.info(self.res.message)
+
+    sampling_subspace.__doc__ = saved.__doc__
+    return sampling_subspace
+
+
+_PATCHED_METHODS = (("construct_lcb_simplicial", "_shgo_b200_saved_lcb", _device_lcb),
+                    ("minimizers", "_shgo_b200_saved_minimizers", _device_minimizers),
+                    ("sampling_subspace", "_shgo_b200_saved_subspace", _device_subspace))
+
+
 def install(driver=None):
     """Rebind ``Complex`` in the driver module to DeviceComplex (what INTEGRATION.md asks a
     reference maintainer to do in one line).  Returns the driver module.  This is a process-wide
@@ -72,10 +128,11 @@ def install(driver=None):
             m._shgo_b200_saved_complex = m.Complex
             m.Complex = _cx.DeviceComplex
         _cx.DeviceComplex.scipy_constraint_rule = m.__name__.startswith("scipy.")
-        if not hasattr(m.SHGO, "_shgo_b200_saved_lcb"):
-            saved = m.SHGO.construct_lcb_simplicial
-            m.SHGO._shgo_b200_saved_lcb = saved
-            m.SHGO.construct_lcb_simplicial = _device_lcb(saved)
+        for name, slot, make in _PATCHED_METHODS:
+            if not hasattr(m.SHGO, slot):
+                saved = getattr(m.SHGO, name)
+                setattr(m.SHGO, slot, saved)
+                setattr(m.SHGO, name, make(saved))
         return m
 
 
@@ -86,9 +143,10 @@ def uninstall(driver=None):
         if saved is not None:
             m.Complex = saved
             del m._shgo_b200_saved_complex
-        if hasattr(m.SHGO, "_shgo_b200_saved_lcb"):
-            m.SHGO.construct_lcb_simplicial = m.SHGO._shgo_b200_saved_lcb
-            del m.SHGO._shgo_b200_saved_lcb
+        for name, slot, _ in _PATCHED_METHODS:
+            if hasattr(m.SHGO, slot):
+                setattr(m.SHGO, name, getattr(m.SHGO, slot))
+                delattr(m.SHGO, slot)
         _cx.DeviceComplex.scipy_constraint_rule = False
         return m
 
@@ -180,8 +238,9 @@ def SHGO(func, bounds, args=(), constraints=None, n=None, iters=None, callback=N
                          workers=workers)
         finally:
             _cx.set_pending_sampler(None)
-        saved = getattr(m.SHGO, "_shgo_b200_saved_lcb", m.SHGO.construct_lcb_simplicial)
-    obj.construct_lcb_simplicial = types.MethodType(_device_lcb(saved), obj)
+        saved = {name: getattr(m.SHGO, slot, getattr(m.SHGO, name)) for name, slot, _ in _PATCHED_METHODS}
+    for name, _, make in _PATCHED_METHODS:
+        setattr(obj, name, types.MethodType(make(saved[name]), obj))
     obj.HC.scipy_constraint_rule = m.__name__.startswith("scipy.")
     return obj
 

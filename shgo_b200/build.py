@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libshgo_b200.so")
-SOURCES = ["eval.cu", "graph.cu", "star.cu", "reorder.cu", "lattice.cu", "bounds.cu", "ctx.cu"]
+SOURCES = ["eval.cu", "graph.cu", "star.cu", "reorder.cu", "pool.cu", "lattice.cu", "bounds.cu", "ctx.cu"]
 HEADERS = ["common.cuh", "sources.cuh", "functors.cuh", os.path.join("..", "..", "include", "shgo_b200.h")]
 
 # -fmad=false: the reference's arithmetic is numpy's (never fused); FMAs are written explicitly

@@ -313,6 +313,7 @@ class DeviceComplex:
         self._epoch = 0              # classifications done so far
         self.argmin_index = -1
         self.pool_indices = np.zeros(0, np.int64)
+        self._pool_cache_order = np.zeros(0, np.int64)
 
     # =====================================================================================
     # graph construction entry points (what SHGO.iterate_hypercube / iterate_delaunay call)
@@ -588,7 +589,24 @@ class DeviceComplex:
             # that order and minimise_pool starts from X_min[0] (_shgo.py:1146-1152,1177)
             r = self._rank[torch.from_numpy(want).to(self.device)].cpu().numpy()
             want = want[np.argsort(r, kind="stable")]
-        self._materialise(want, pool_set=set(pool.tolist()))
+        pool_set = set(pool.tolist())
+        self._pool_cache_order = np.array([i for i in want.tolist() if i in pool_set], np.int64)
+        self._materialise(want, pool_set=pool_set)
+
+    def ranked_pool(self, xl_maps=(), by="f", xref=None):
+        """SURVEY.md section 8(f)-3 on the device: the minimiser pool without the vertices whose
+        coordinates equal an earlier local minimum (`xl_maps`, SHGO.minimizers _shgo.py:1116-1122),
+        ordered by f (sort_min_pool, _shgo.py:1213-1219) or by distance from `xref` (g_topograph,
+        _shgo.py:1227-1243); equal keys keep the reference's cache order.  -> vertex ids."""
+        self._process()
+        ids = self._pool_cache_order
+        if len(ids) == 0:
+            return ids
+        t = torch.from_numpy(ids).to(self.device)
+        x = torch.from_numpy(np.ascontiguousarray(self._coordinates(ids).T)).to(self.device)
+        local = hp.pool_rank(torch.arange(len(ids), device=self.device), self._f[t].contiguous(), x,
+                             [np.asarray(v, np.float64) for v in xl_maps], by=by, xref=xref)
+        return ids[local.cpu().numpy()]
 
     def _materialise(self, ids, pool_set=None, listed=True):
         if len(ids) == 0:
@@ -789,6 +807,32 @@ class DeviceComplex:
         if s.host.shape != pts.shape or not np.array_equal(pts, s.host):
             return None
         return s.tab
+
+
+def device_sampling_subspace(C, g_cons, g_args, device=None):
+    """SHGO.sampling_subspace (_shgo.py:1452-1463) on the device when every constraint can be
+    evaluated there (a registered constraint set, or callables marked torch-vectorised); returns the
+    filtered C-order array, or None when the constraints are plain host callables."""
+    if not g_cons:
+        return None
+    C = np.ascontiguousarray(C, np.float64)
+    n, d = C.shape
+    gid = F.constraint_set_id(g_cons, g_args)
+    torch_ok = all(_is_torch_vectorized(g) for g in g_cons)
+    if not ((gid is not None and gid != F.G_NONE) or torch_ok) or n == 0:
+        return None
+    dev = hp._dev(device)
+    x = torch.from_numpy(C).to(dev).t().contiguous()
+    if torch_ok:
+        g = torch.stack([torch.as_tensor(gc(x, *ga), dtype=torch.float64, device=dev).expand(n).contiguous()
+                         for gc, ga in zip(g_cons, g_args)])
+    else:
+        # registered sets: the fused kernels give the feasibility flag of the whole set (finite g only,
+        # so the two NaN rules coincide); turn it into a one-row "g" of +-1
+        _, feas = hp.eval_points(F.PAIRED_OBJECTIVE[gid], gid, x)
+        g = (feas.to(torch.float64) * 2.0 - 1.0).reshape(1, n)
+    _, kept = hp.sampling_subspace(x, g)
+    return kept.cpu().numpy()
 
 
 def _never_called(x, *args):  # pragma: no cover

@@ -37,6 +37,12 @@ int sm_count();
 int compact_flags(const uint8_t *flags, uint64_t n, int match, int64_t base, int64_t *idx_out,
                   uint64_t cap, uint64_t *count, void *tmp, cudaStream_t st);
 
+// stable LSD radix sort of (key, id) pairs by 32-bit key, 8 bits per pass (reorder.cu).  Input and
+// result live in (k0, i0); (k1, i1) and hist (radix_hist_bytes(n) bytes) are scratch.
+size_t radix_hist_bytes(uint64_t n);
+int radix_sort_pairs(uint32_t *k0, int32_t *i0, uint32_t *k1, int32_t *i1, uint64_t *hist, uint64_t n,
+                     cudaStream_t st);
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __device__ __forceinline__ double ld_nc_f64(const double *p)

@@ -208,6 +208,33 @@ static inline unsigned grid1d(uint64_t items, int per_sm)
     return (unsigned)(b < 1 ? 1 : b);
 }
 
+size_t radix_hist_bytes(uint64_t n)
+{
+    const uint64_t nblocks = (n + kSortChunk - 1) / kSortChunk;
+    return align256r(256 * (nblocks + 1) * 8);
+}
+
+int radix_sort_pairs(uint32_t *k0, int32_t *i0, uint32_t *k1, int32_t *i1, uint64_t *hist, uint64_t n,
+                     cudaStream_t st)
+{
+    if (n == 0) return SHGO_B200_OK;
+    const uint32_t nblocks = (uint32_t)((n + kSortChunk - 1) / kSortChunk);
+    // 4 passes: (k0, i0) -> (k1, i1) -> (k0, i0) -> (k1, i1) -> (k0, i0)
+    uint32_t *kin = k0, *kout = k1;
+    int32_t *iin = i0, *iout = i1;
+    for (int pass = 0; pass < 4; ++pass) {
+        radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, n, pass * 8, hist, nblocks);
+        scan_u64_kernel<<<1, 1024, 0, st>>>(hist, 256ull * nblocks);
+        radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, iin, n, pass * 8, hist, nblocks, kout, iout);
+        uint32_t *tk = kin;
+        kin = kout, kout = tk;
+        int32_t *ti = iin;
+        iin = iout, iout = ti;
+    }
+    SHGO_CUDA_TRY(cudaGetLastError());
+    return SHGO_B200_OK;
+}
+
 }  // namespace shgo_b200
 
 using namespace shgo_b200;
@@ -216,9 +243,8 @@ extern "C" {
 
 size_t shgo_b200_morton_workspace(uint64_t n)
 {
-    const uint64_t nblocks = (n + kSortChunk - 1) / kSortChunk;
     // keys x2, ids x1 (the other id buffer is `order`), histogram
-    return 2 * align256r(n * 4) + align256r(n * 4) + align256r(256 * (nblocks + 1) * 8);
+    return 2 * align256r(n * 4) + align256r(n * 4) + radix_hist_bytes(n);
 }
 
 int shgo_b200_morton_order(const double *x_soa, uint64_t ld, int d, uint64_t n, const double *lb,
@@ -242,20 +268,8 @@ int shgo_b200_morton_order(const double *x_soa, uint64_t ld, int d, uint64_t n, 
     int32_t *i1 = reinterpret_cast<int32_t *>(p);
     p += align256r(n * 4);
     uint64_t *hist = reinterpret_cast<uint64_t *>(p);
-    const uint32_t nblocks = (uint32_t)((n + kSortChunk - 1) / kSortChunk);
     morton_key_kernel<<<grid1d(n, 8), 256, 0, st>>>(x_soa, ld, d, n, lb, ub, k0, order);
-    // 4 passes: (k0, order) -> (k1, i1) -> (k0, order) -> (k1, i1) -> (k0, order)
-    uint32_t *kin = k0, *kout = k1;
-    int32_t *iin = order, *iout = i1;
-    for (int pass = 0; pass < 4; ++pass) {
-        radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, n, pass * 8, hist, nblocks);
-        scan_u64_kernel<<<1, 1024, 0, st>>>(hist, 256ull * nblocks);
-        radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, iin, n, pass * 8, hist, nblocks, kout, iout);
-        uint32_t *tk = kin;
-        kin = kout, kout = tk;
-        int32_t *ti = iin;
-        iin = iout, iout = ti;
-    }
+    if (int rc = radix_sort_pairs(k0, order, k1, i1, hist, n, st)) return rc;
     if (newid) invert_perm_kernel<<<grid1d(n, 8), 256, 0, st>>>(order, n, newid);
     SHGO_CUDA_TRY(cudaGetLastError());
     return SHGO_B200_OK;

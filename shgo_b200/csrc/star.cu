@@ -309,7 +309,7 @@ __device__ __forceinline__ void star_funnel(const int32_t *__restrict__ sc, cons
 //                middle part once and then walked exactly like a single-GPU row.
 // BULK         : stage with cp.async.bulk + mbarrier, double buffered (see the head of the file).
 // FUSED        : (kLocalEnds only) finish candidates inline over NVLink when their peers are ready.
-constexpr int kBulkThreads = 512, kBulkMinBlocks = 2;    // <= 64 registers
+constexpr int kBulkThreads = 256, kBulkMinBlocks = 5;    // double-buffered variant: same budget
 constexpr int kPlainThreads = 256, kPlainMinBlocks = 5;  // <= 51 registers, 40 warps per SM
 constexpr int kFusedMinBlocks = 4;                       // fused remote reads hold 4 values: <= 64 registers
 

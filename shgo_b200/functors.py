@@ -161,3 +161,8 @@ def constraint_set_id(g_cons, g_args=None):
     if [t for t in tags] == [(gid, i) for i in range(_GSET_SIZE[gid])]:
         return gid
     return None
+
+
+# objective functor compiled together with each constraint set (csrc/eval.cu dispatch table): lets a
+# caller that only wants the feasibility flags of a registered set run the fused kernel
+PAIRED_OBJECTIVE = {G_CATTLE_FEED: F_CATTLE_FEED, G_SUM_LE_6: F_SPHERE}

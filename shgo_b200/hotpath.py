@@ -136,6 +136,53 @@ def mask_infeasible(f, g=None, feasible=None):
     return f, feasible
 
 
+def sampling_subspace(x_soa, g):
+    """SHGO.sampling_subspace (_shgo.py:1452-1463) on the device: x_soa (d, n) sample points, g (m, n)
+    constraint values.  -> (kept row indices int64, kept points as a C-order (m', d) tensor); a point
+    survives iff every g >= 0.0 (NaN drops it)."""
+    d, n = x_soa.shape
+    dev = x_soa.device
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    m = 0 if g is None else g.shape[0]
+    if g is not None:
+        g = g.contiguous()
+        assert g.dtype == torch.float64 and g.shape[1] == n
+    _lib.call("shgo_b200_subspace_mask", _ptr(g), m, n, _ptr(keep), _stream())
+    idx, cnt = compact_pool(keep)
+    k = int(cnt.item())
+    idx = idx[:k]
+    out = torch.empty((k, d), dtype=torch.float64, device=dev)
+    _lib.call("shgo_b200_gather_rows", _ptr(x_soa), soa_ld(x_soa), d, _ptr(idx), k, _ptr(out), _stream())
+    return idx, out
+
+
+def pool_rank(pool, f, x_soa=None, xl=None, by="f", xref=None):
+    """The minimiser pool after SHGO.minimizers' post-processing (_shgo.py:1116-1122, 1213-1219) or
+    g_topograph (_shgo.py:1227-1243): `pool` (vertex ids, the reference's cache order) without the
+    vertices whose coordinates equal a row of `xl`, ordered by f (by='f') or by the euclidean distance
+    from `xref` (by='distance'); equal keys keep the pool's order.  -> int64 tensor of vertex ids."""
+    dev = f.device
+    pool = pool.to(device=dev, dtype=torch.int64).contiguous()
+    m = pool.numel()
+    d = x_soa.shape[0] if x_soa is not None else 1
+    k = 0
+    if xl is not None and len(xl):
+        xl = torch.as_tensor(np.asarray(xl, np.float64).reshape(-1, d), device=dev).contiguous()
+        k = xl.shape[0]
+    else:
+        xl = None
+    mode = {"f": 0, "distance": 1}[by]
+    if xref is not None:
+        xref = torch.as_tensor(np.asarray(xref, np.float64).reshape(d), device=dev).contiguous()
+    ranked = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _lib.lib().shgo_b200_pool_rank_workspace(m)
+    tmp = torch.empty(ws, dtype=torch.uint8, device=dev)
+    _lib.call("shgo_b200_pool_rank", _ptr(pool), m, _ptr(f), _ptr(x_soa), soa_ld(x_soa) if x_soa is not None else 0,
+              d, _ptr(xl), k, mode, _ptr(xref), _ptr(ranked), _ptr(count), _ptr(tmp), ws, _stream())
+    return ranked[: int(count.item())]
+
+
 def csr_from_simplices(simplices, n):
     """Symmetric CSR (row_ptr int64 [n+1], col int32 [nnz]) of the reference's vertex graph."""
     assert simplices.dtype == torch.int32 and simplices.dim() == 2

@@ -144,6 +144,32 @@ def shgo_b200_publish_ready(peer_flags, npeers, me, epoch, stream):
     _req(peer_flags and 1 <= npeers <= 32 and me >= 0, "bad arguments")
 
 
+def shgo_b200_subspace_mask(g, m, n, keep, stream):
+    if n == 0:
+        return
+    _req(keep, "null output")
+    _req(m == 0 or g, "m > 0 but g is null")
+
+
+def shgo_b200_gather_rows(x_soa, ld, d, idx, m, out, stream):
+    _req(d >= 1, "d must be positive (got %d)", d)
+    if m == 0:
+        return
+    _req(x_soa and idx and out, "null pointer")
+
+
+def shgo_b200_pool_rank(pool, m, f, x_soa, ld, d, xl, k, mode, xref, ranked, count, tmp, tmp_bytes, stream):
+    _req(count, "null count")
+    _req(d >= 1 and k >= 0 and mode in (0, 1), "bad arguments")
+    if m == 0:
+        return
+    _req(pool and ranked and tmp, "null pointer")
+    _req(mode == 1 or f, "null f")
+    _req((k == 0 and mode == 0) or x_soa, "coordinates needed")
+    _req(k == 0 or xl, "null xl")
+    _req(mode == 0 or xref, "null xref")
+
+
 def shgo_b200_compact_pool(is_min, n, base, idx_out, cap, count, tmp, tmp_bytes, stream):
     _req(count and tmp, "null pointer")
     _req(is_min or n == 0, "null flags")

@@ -87,6 +87,18 @@ def scatter_u8(src, idx, out):
     return out
 
 
+def sampling_subspace(x_soa, g):
+    C = np.ascontiguousarray(x_soa.numpy().T)
+    keep = np.ones(C.shape[0], bool) if g is None else np.all(g.numpy() >= 0.0, axis=0)
+    return torch.from_numpy(np.flatnonzero(keep)), torch.from_numpy(np.ascontiguousarray(C[keep]))
+
+
+def pool_rank(pool, f, x_soa=None, xl=None, by="f", xref=None):
+    x = None if x_soa is None else np.ascontiguousarray(x_soa.numpy().T)
+    out = orc.pool_rank(pool.numpy(), f.numpy(), x, [] if xl is None else xl, by=by, xref=xref)
+    return torch.from_numpy(np.ascontiguousarray(out))
+
+
 def count_nfev(row_ptr, feasible=None, out=None):
     c = orc.nfev(row_ptr.numpy(), None if feasible is None else feasible.numpy())
     return torch.tensor([int(c)], dtype=torch.int64)
@@ -271,7 +283,7 @@ def install(monkeypatch):
     """Patch shgo_b200.hotpath in place (functions are looked up as attributes at call time)."""
     from shgo_b200 import hotpath as hp
     for name in ("SobolTables", "sobol_points", "eval_sobol", "eval_points", "mask_infeasible",
-                 "csr_from_simplices", "count_nfev", "morton_order", "relabel3", "gather", "scatter_u8", "first_seen", "star_csr", "star_csr_shard", "PoolWorkspace", "compact_pool", "argmin", "lattice_eval",
+                 "csr_from_simplices", "sampling_subspace", "pool_rank", "count_nfev", "morton_order", "relabel3", "gather", "scatter_u8", "first_seen", "star_csr", "star_csr_shard", "PoolWorkspace", "compact_pool", "argmin", "lattice_eval",
                  "lattice_coords", "lattice_star", "local_bounds_csr", "lattice_local_bounds", "lattice_eval_push"):
         obj = globals()[name]
         real = getattr(hp, name)

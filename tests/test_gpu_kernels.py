@@ -770,3 +770,51 @@ def test_argmin_breaks_ties_by_rank(hp):
     r = torch.arange(1 << 20, 0, -1, dtype=torch.int64, device="cuda")
     assert hp.argmin(big, None, r)[0] == (1 << 20) - 1 and hp.argmin(big)[0] == 0
     assert hp.argmin(torch.full((10,), float("inf"), dtype=torch.float64, device="cuda")) == (-1, float("inf"))
+
+
+def test_sampling_subspace_on_the_device(hp):
+    """row a4': C = C[g(C.T) >= 0.0] for every g (reference _shgo.py:1452-1463); NaN drops the point"""
+    from shgo_b200 import functors as F
+    n, d = 5000, 4
+    tab = hp.SobolTables([(0.0, 1.0)] * d)
+    x = hp.sobol_points(tab, 0, n, "soa")
+    C = x.t().contiguous().cpu().numpy()
+    gs = (F.cattle_feed_g1, F.cattle_feed_g2)
+    g = torch.stack([torch.from_numpy(np.asarray(gi(C.T))).cuda() for gi in gs])
+    g[0, 7] = float("nan")
+    g[1, 11] = -0.0                                     # -0.0 >= 0.0 is True
+    idx, kept = hp.sampling_subspace(x, g)
+    gh = g.cpu().numpy()
+    ref_keep = np.all(gh >= 0.0, axis=0)
+    assert not ref_keep[7]
+    assert np.array_equal(idx.cpu().numpy(), np.flatnonzero(ref_keep))
+    assert np.array_equal(kept.cpu().numpy(), C[ref_keep])
+    idx2, C2 = orc.sampling_subspace(C, gs)             # the reference's own loop
+    ok = np.ones(n, bool); ok[7] = False
+    assert np.array_equal(np.intersect1d(idx2, np.flatnonzero(ok)), np.intersect1d(idx.cpu().numpy(), np.flatnonzero(ok)))
+    e_idx, e_pts = hp.sampling_subspace(x[:, :0].contiguous(), None)
+    assert e_idx.numel() == 0 and e_pts.shape == (0, d)
+
+
+@pytest.mark.parametrize("m,ties", [(1, False), (40, False), (5000, True), (300000, True)])
+def test_pool_rank_on_the_device(hp, m, ties):
+    """row f3: LMC exclusion by coordinates + f-sorted pool + distance-sorted pool"""
+    rng = np.random.default_rng(m)
+    n, d = max(4 * m, 64), 3
+    x = rng.uniform(-5, 5, (n, d))
+    f = rng.standard_normal(n)
+    if ties:
+        f = np.round(f, 2)                              # many exactly equal values
+    f[rng.integers(0, n, 5)] = np.inf
+    f[0] = -0.0
+    pool = np.sort(rng.choice(n, m, replace=False))
+    xl = [x[pool[len(pool) // 2]].copy(), x[pool[0]].copy(), np.array([9.0, 9.0, 9.0])]
+    xs = torch.from_numpy(x).cuda().t().contiguous()
+    fd = torch.from_numpy(f).cuda()
+    pd = torch.from_numpy(pool).cuda()
+    got = hp.pool_rank(pd, fd, xs, xl).cpu().numpy()
+    assert np.array_equal(got, orc.pool_rank(pool, f, x, xl))
+    assert np.array_equal(hp.pool_rank(pd, fd).cpu().numpy(), orc.pool_rank(pool, f))
+    xref = x[pool[-1]]
+    got = hp.pool_rank(pd, fd, xs, xl[:1], by="distance", xref=xref).cpu().numpy()
+    assert np.array_equal(got, orc.pool_rank(pool, f, x, xl[:1], by="distance", xref=xref))

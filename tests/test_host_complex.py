@@ -257,3 +257,41 @@ def test_mesh_classified_in_morton_numbering_gives_the_same_result(sb, monkeypat
     assert used, "the Z-order numbering was not exercised"
     assert (plain.nfev, plain.nit, plain.nlfev) == (morton.nfev, morton.nit, morton.nlfev)
     assert np.array_equal(plain.xl, morton.xl) and np.array_equal(plain.funl, morton.funl)
+
+
+def test_large_pools_are_ranked_on_the_device_with_the_same_outcome(sb, monkeypatch):
+    """SHGO.minimizers' LMC exclusion + f-ordering served by DeviceComplex.ranked_pool
+    (threshold forced to 0 here): same result as the driver's own loop + np.argsort."""
+    from shgo_b200 import api, functors as F
+    bounds = [(-5.12, 4.7), (-4.9, 5.12)]                 # no symmetry: no exactly equal f values
+    kw = dict(n=None, iters=3, sampling_method="simplicial")
+    plain = sb.shgo(F.rastrigin, bounds, **kw)
+    monkeypatch.setattr(api, "DEVICE_POOL_RANK_MIN", 0)
+    used = []
+    real = api._cx.DeviceComplex.ranked_pool
+    monkeypatch.setattr(api._cx.DeviceComplex, "ranked_pool",
+                        lambda self, *a, **k: used.append(1) or real(self, *a, **k))
+    dev = sb.shgo(F.rastrigin, bounds, **kw)
+    assert used
+    assert (plain.nfev, plain.nit, plain.nlfev, plain.success) == (dev.nfev, dev.nit, dev.nlfev, dev.success)
+    assert np.array_equal(plain.xl, dev.xl) and np.array_equal(plain.funl, dev.funl)
+    kw = dict(n=256, iters=2, sampling_method="sobol")
+    plain2 = _reference_run(F.styblinski_tang, [(-5.0, 4.0)] * 3, **kw)
+    dev2 = sb.shgo(F.styblinski_tang, [(-5.0, 4.0)] * 3, **kw)
+    assert np.array_equal(plain2.xl, dev2.xl) and plain2.nfev == dev2.nfev
+
+
+def test_sampling_subspace_served_by_the_device(sb, monkeypatch):
+    """row a4': options['infty_constraints'] = False makes the driver drop infeasible samples before
+    triangulating (_shgo.py:1452-1463); with a registered constraint set that filter runs on the device"""
+    from shgo_b200 import api, functors as F
+    cons = ({"type": "ineq", "fun": F.cattle_feed_g1}, {"type": "ineq", "fun": F.cattle_feed_g2})
+    kw = dict(n=128, iters=1, sampling_method="sobol", constraints=cons, options={"infty_constraints": False})
+    ref = _reference_run(F.cattle_feed, [(0.0, 1.0)] * 4, **kw)
+    used = []
+    real = api._cx.device_sampling_subspace
+    monkeypatch.setattr(api._cx, "device_sampling_subspace", lambda *a, **k: used.append(1) or real(*a, **k))
+    res = sb.shgo(F.cattle_feed, [(0.0, 1.0)] * 4, **kw)
+    assert used
+    assert (res.nfev, res.nit, res.success) == (ref.nfev, ref.nit, ref.success)
+    np.testing.assert_allclose(res.x, ref.x, rtol=1e-9, atol=1e-12)
