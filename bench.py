@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--e2e-log2n", type=int, default=26,
                     help="log2 n of the host-buffer (e2e) leg AND of the CPU arm's sample (same problem in both)")
     ap.add_argument("--cpu-log2n", type=int, default=None, help="override the CPU sample size (default: --e2e-log2n)")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "p2p", "allgather"],
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "fused", "allgather"],
                     help="how neighbour f values cross GPUs (N > 1)")
     ap.add_argument("--chunks", type=int, default=1, help="p2p exchange: classify the shard in chunks (overlap)")
     ap.add_argument("--phase1-warps", type=int, default=0, help="p2p + chunks: resident warps per SM of phase 1")

@@ -32,18 +32,13 @@ namespace shgo_b200 {
 
 constexpr int kMaxStarWarps = 16384;  // upper bound on the warps of one launch (candidate segments)
 // Candidate workspace written by phase 1 (uint32 words):
-//   [0] warps  [1] id-segment capacity  [2] record-segment capacity (0: no records)  [3] -
+//   [0] warps  [1] id-segment capacity  [2], [3] -
 //   [4 .. 4+kMaxStarWarps)  candidates per warp
 //   id segments    warps x seg_cap   row ids (relative to row0), dense per warp
-//   record segments warps x rec_cap x 8 words, 32-byte aligned: {row, nrem, f lo, f hi, id0..id3} for the
-//                  first rec_cap candidates of a warp (kLocalEnds only): everything phase 2 needs, so
-//                  that it touches no row_ptr / col / f of its own -- only the list and the peers
+// (Appending a 32-byte record {row, f, remote neighbour ids} per candidate, so that phase 2 touches
+// no row_ptr / col / f of its own, was measured: phase 2 alone 0.18 -> 0.08 ms with all shards local,
+// but phase 1 +0.07 ms and the real 8-GPU step 1.38 -> 1.44 ms -- phase 2 is bound by NVLink there.)
 constexpr int kCandHeader = 4;
-constexpr uint32_t kRecWords = 8, kRecSlow = 255;
-__host__ __device__ inline uint64_t cand_rec_base(uint64_t nw, uint64_t seg_cap)
-{
-    return (kCandHeader + (uint64_t)kMaxStarWarps + nw * seg_cap + 7) & ~7ull;
-}
 constexpr unsigned kFull = 0xffffffffu;
 
 // ---- cache policies and flavoured loads ----------------------------------------------------------
@@ -69,6 +64,11 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
 {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -311,7 +311,14 @@ __device__ __forceinline__ void star_funnel(const int32_t *__restrict__ sc, cons
 // FUSED        : (kLocalEnds only) finish candidates inline over NVLink when their peers are ready.
 constexpr int kBulkThreads = 256, kBulkMinBlocks = 5;    // double-buffered variant: same budget
 constexpr int kPlainThreads = 256, kPlainMinBlocks = 5;  // <= 51 registers, 40 warps per SM
-constexpr int kFusedMinBlocks = 4;                       // fused remote reads hold 4 values: <= 64 registers
+constexpr int kFusedMinBlocks = 5;
+// FUSED: remote reads in flight.  A candidate's remote neighbours are fetched over NVLink by cp.async
+// (LDGSTS) straight into a slot of a per-warp ring in shared memory -- no register is held while the
+// request crosses the switch -- one commit group per tile, consumed kFusedDepth-1 tiles later
+// (cp.async.wait_group).  8 slots per tile and warp (a tile has ~1.2 candidates on the bench graph).
+constexpr int kFusedDepth = 4, kFusedSlots = 8, kInline = 4;
+constexpr int kSlotDoubles = 2 + kInline;  // {row | -, f of the row, up to 4 neighbour values}
+constexpr size_t kFusedRingBytes = (size_t)kFusedDepth * kFusedSlots * kSlotDoubles * sizeof(double);
 
 template <int MODE, int STAGE, bool FUSED, int MAXLG>
 __global__ void __launch_bounds__(STAGE == 1 ? kBulkThreads : kPlainThreads,
@@ -325,8 +332,11 @@ star_kernel(const StarParams p)
     constexpr int NBUF = DOUBLE ? 2 : 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int cap_w = p.cap_w;
+    static_assert(!FUSED || (STAGE == 2 && MODE == kLocalEnds), "FUSED: bulk staging, remote_at_ends rows");
     int32_t *buf0 = star_smem + (size_t)wid * NBUF * cap_w;
     uint64_t *bars = reinterpret_cast<uint64_t *>(star_smem + (size_t)nwarp * NBUF * cap_w) + wid * 2;
+    double *ring = reinterpret_cast<double *>(reinterpret_cast<uint64_t *>(star_smem + (size_t)nwarp * NBUF * cap_w) +
+                                              nwarp * 2) + (size_t)wid * (kFusedRingBytes / sizeof(double));
     const int64_t *__restrict__ row_ptr = p.row_ptr;
     const int32_t *__restrict__ col = p.col;
     const double *__restrict__ f = p.f;
@@ -341,10 +351,7 @@ star_kernel(const StarParams p)
     // that phase 2 needs no compaction pass: [0] = warps, [1] = segment capacity,
     // [2 .. 2+kMaxStarWarps) = per-warp counts, then the segments
     const uint32_t seg_cap = (uint32_t)(((ntiles + nw - 1) / nw) << 5);
-    const uint32_t rec_cap = MODE == kLocalEnds ? seg_cap >> 2 : 0;
     uint32_t *seg = (LOCAL && p.cand_ws) ? p.cand_ws + kCandHeader + kMaxStarWarps + gw * (uint64_t)seg_cap : nullptr;
-    uint32_t *rec = (LOCAL && p.cand_ws) ? p.cand_ws + cand_rec_base(nw, seg_cap) + gw * (uint64_t)rec_cap * kRecWords
-                                         : nullptr;
     uint32_t ncand = 0;
     const uint64_t stream_pol = l2_evict_first_policy(), keep = l2_evict_last_policy();
 
@@ -375,25 +382,34 @@ star_kernel(const StarParams p)
                 for (int v = lane; v < nvec; v += 32) cp_async16(dst + (v << 2), src + (v << 2), stream_pol);
             }
             const int t = (nvec << 2) + lane;  // the <= 3 words behind the last whole vector
-            if (t < s.len) cp_async4(dst + t, src + t);
+            if (FUSED) {  // cp.async groups count the remote reads there: plain load + store
+                if (t < s.len) dst[t] = __ldg(src + t);
+            } else if (t < s.len) {
+                cp_async4(dst + t, src + t);
+            }
         }
-        cp_async_commit();
+        if (!FUSED) cp_async_commit();
     };
 
-    // pending inline remote reads of the previous tile (FUSED): the lane that owns a candidate row
-    // holds up to kInline remote neighbours' values (+inf where it has fewer) until the next tile is done
-    constexpr int kInline = 4;
-    double pend_v[kInline], pend_fv = 0.0;
+    // FUSED: ring of pending remote reads, see kFusedDepth
+    int head = 0;
+    if (FUSED) {
+        for (int i = lane; i < kFusedDepth * kFusedSlots; i += 32)
+            reinterpret_cast<uint32_t *>(ring + i * kSlotDoubles)[0] = 0xffffffffu;
+        __syncwarp();
+    }
+    auto resolve_stage = [&](int st) {  // the values of every slot of stage `st` have arrived
+        if (lane < kFusedSlots) {
+            double *sl = ring + (st * kFusedSlots + lane) * kSlotDoubles;
+            const uint32_t row = reinterpret_cast<uint32_t *>(sl)[0];
+            if (row != 0xffffffffu) {
+                const double fvs = sl[1];
+                bool good = true;
 #pragma unroll
-    for (int u = 0; u < kInline; ++u) pend_v[u] = pos_inf();
-    uint32_t pend_row = 0xffffffffu;  // tile-local row id of the candidate this lane is finishing
-    auto resolve_pending = [&]() {
-        if (pend_row != 0xffffffffu) {
-            bool good = true;
-#pragma unroll
-            for (int u = 0; u < kInline; ++u) good = good && (pend_fv < pend_v[u]);
-            p.is_min[pend_row] = good ? 1 : 0;
-            pend_row = 0xffffffffu;
+                for (int u = 0; u < kInline; ++u) good = good && (fvs < sl[2 + u]);
+                p.is_min[row] = good ? 1 : 0;
+                reinterpret_cast<uint32_t *>(sl)[0] = 0xffffffffu;
+            }
         }
     };
 
@@ -437,7 +453,7 @@ star_kernel(const StarParams p)
         const int32_t *sc = buf0 + pb * cap_w;
         if (s.staged) {
             if (DOUBLE) cp_async_wait<1>();  // this tile's tail words (the newest group is the next tile's)
-            else cp_async_wait<0>();
+            else if (!FUSED) cp_async_wait<0>();
             if (BULK && (s.len >> 2) > 0) {
                 mbar_wait(bars + pb, (phase_bits >> pb) & 1u);
                 phase_bits ^= 1u << pb;
@@ -473,13 +489,11 @@ star_kernel(const StarParams p)
         bool candidate = LOCAL && valid && ok && remote;
         bool written_later = false;
         if (FUSED) {
-            // previous tile's remote values have had a whole tile to arrive
-            resolve_pending();
             if (poll) ready_mask = __ballot_sync(kFull, lane < p.nshards && (int32_t)(flag_word - p.epoch) >= 0);
             const int nlo = kt - k0, nrem = nlo + (le0 - let);
-            if (candidate && s.staged && nrem <= kInline) {
-                uint32_t w[kInline];
-                bool rdy = true;
+            uint32_t w[kInline];
+            bool rdy = candidate && s.staged && nrem <= kInline;
+            if (rdy) {
 #pragma unroll
                 for (int u = 0; u < kInline; ++u) {
                     w[u] = u < nrem ? (uint32_t)sc[u < nlo ? k0 + u : let + (u - nlo)] : 0u;
@@ -488,41 +502,36 @@ star_kernel(const StarParams p)
                     // iteration is intact until it has passed the next barrier, which waits for this GPU)
                     rdy = rdy && (u >= nrem || ((ready_mask >> q) & 1u));
                 }
-                if (rdy) {
-#pragma unroll
-                    for (int u = 0; u < kInline; ++u) {
-                        const uint32_t q = p.shard_shift >= 0 ? (w[u] >> p.shard_shift) : (w[u] / p.rows_per_shard);
-                        pend_v[u] = u < nrem ? ld_peer_f64(p.shards[q] + (w[u] - q * p.rows_per_shard)) : pos_inf();
-                    }
-                    pend_fv = fv;
-                    pend_row = (uint32_t)lr;
-                    candidate = false;  // not for phase 2
-                    written_later = true;
-                }
             }
+            const unsigned cb = __ballot_sync(kFull, rdy);
+            const int slot = __popc(cb & ((1u << lane) - 1u));
+            if (rdy && slot < kFusedSlots) {
+                double *sl = ring + (head * kFusedSlots + slot) * kSlotDoubles;
+                reinterpret_cast<uint32_t *>(sl)[0] = (uint32_t)lr;
+                sl[1] = fv;
+#pragma unroll
+                for (int u = 0; u < kInline; ++u) {
+                    if (u < nrem) {
+                        const uint32_t q = p.shard_shift >= 0 ? (w[u] >> p.shard_shift) : (w[u] / p.rows_per_shard);
+                        cp_async8(sl + 2 + u, p.shards[q] + (w[u] - q * p.rows_per_shard));
+                    } else {
+                        sl[2 + u] = pos_inf();
+                    }
+                }
+                candidate = false;  // finished here, not by phase 2
+                written_later = true;
+            }
+            cp_async_commit();
+            cp_async_wait<kFusedDepth - 1>();  // the group committed kFusedDepth-1 tiles ago is complete
+            __syncwarp();
+            resolve_stage((head + 1) % kFusedDepth);
+            head = (head + 1) % kFusedDepth;
         }
         if (valid && !written_later) p.is_min[lr] = ok ? (candidate ? 2 : 1) : 0;
         if (LOCAL && seg != nullptr) {
             const unsigned m = __ballot_sync(kFull, candidate);
             const uint32_t pos = ncand + __popc(m & ((1u << lane) - 1u));
             if (candidate) seg[pos] = (uint32_t)lr;
-            if (MODE == kLocalEnds && candidate && pos < rec_cap) {
-                const int nlo = kt - k0, nrem = nlo + (le0 - let);
-                uint4 a, b4 = make_uint4(0, 0, 0, 0);
-                a.x = (uint32_t)lr;
-                a.y = (s.staged && nrem <= 4) ? (uint32_t)nrem : kRecSlow;
-                a.z = (uint32_t)__double2loint(fv);
-                a.w = (uint32_t)__double2hiint(fv);
-                if (a.y != kRecSlow) {
-                    uint32_t id[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) id[u] = u < nrem ? (uint32_t)sc[u < nlo ? k0 + u : let + (u - nlo)] : 0u;
-                    b4 = make_uint4(id[0], id[1], id[2], id[3]);
-                }
-                uint4 *dst = reinterpret_cast<uint4 *>(rec + (uint64_t)pos * kRecWords);
-                dst[0] = a;
-                dst[1] = b4;
-            }
             ncand += __popc(m);
         }
         __syncwarp();  // the buffer is rewritten by a later tile
@@ -537,13 +546,16 @@ star_kernel(const StarParams p)
         }
     }
     if (DOUBLE) cp_async_wait<0>();
-    if (FUSED) resolve_pending();
+    if (FUSED) {
+        cp_async_wait<0>();
+        __syncwarp();
+        for (int st = 0; st < kFusedDepth; ++st) resolve_stage(st);
+    }
     if (LOCAL && seg != nullptr && lane == 0) {
         p.cand_ws[kCandHeader + gw] = ncand;
         if (gw == 0) {
             p.cand_ws[0] = (uint32_t)nw;
             p.cand_ws[1] = seg_cap;
-            p.cand_ws[2] = rec_cap;
         }
     }
     if (p.nfev != nullptr) {
@@ -648,44 +660,22 @@ star_remote_kernel(const int64_t *__restrict__ cand, const uint64_t *__restrict_
                         is_min);
 }
 
-// candidates from the per-warp segments phase 1 wrote: no compaction pass in between.  Where phase 1
-// left a record (row, f, remote neighbour ids) the row is finished from the record alone: a coalesced
-// read of the list, the NVLink reads, one flag byte -- no row_ptr / col / f traffic of its own.
+// candidates from the per-warp segments phase 1 wrote: no compaction pass in between
 __global__ void __launch_bounds__(256)
 star_remote_seg_kernel(const uint32_t *__restrict__ cand_ws, const int64_t *__restrict__ row_ptr,
                        const int32_t *__restrict__ col, ShardedF facc, const double *__restrict__ f_own,
                        uint64_t own0, uint64_t own_rows, uint64_t row0, int remote_at_ends,
                        uint8_t *__restrict__ is_min)
 {
-    const uint32_t nw = cand_ws[0], seg_cap = cand_ws[1], rec_cap = cand_ws[2];
+    const uint32_t nw = cand_ws[0], seg_cap = cand_ws[1];
     const int lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t *recs = cand_ws + cand_rec_base(nw, seg_cap);
     for (uint32_t sw = gw; sw < nw; sw += tw) {
         const uint32_t n = cand_ws[kCandHeader + sw];
-        const uint32_t nrec = n < rec_cap ? n : rec_cap;
         const uint32_t *seg = cand_ws + kCandHeader + kMaxStarWarps + sw * (uint64_t)seg_cap;
-        const uint4 *rec = reinterpret_cast<const uint4 *>(recs + sw * (uint64_t)rec_cap * kRecWords);
-        for (uint32_t i = lane; i < n; i += 32) {
-            if (i < nrec) {
-                const uint4 a = __ldg(rec + 2 * i);
-                if (a.y != kRecSlow) {
-                    const uint4 b = __ldg(rec + 2 * i + 1);
-                    const double fv = __hiloint2double((int)a.w, (int)a.z);
-                    const uint32_t id[4] = {b.x, b.y, b.z, b.w};
-                    double fn[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) fn[u] = (uint32_t)u < a.y ? facc((int32_t)id[u]) : pos_inf();
-                    bool ok = true;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) ok = ok && (fv < fn[u]);
-                    is_min[a.x] = ok ? 1 : 0;
-                    continue;
-                }
-            }
+        for (uint32_t i = lane; i < n; i += 32)
             star_remote_one((uint64_t)seg[i], row_ptr, col, facc, f_own, own0, own_rows, row0, remote_at_ends,
                             is_min);
-        }
     }
 }
 
@@ -743,7 +733,7 @@ static int launch_star_t(const StarParams &p0, uint64_t nnz_hint, int warps_req,
     p.cap_w = (int)cap;
     constexpr int NBUF = STAGE == 1 ? 2 : 1;
     constexpr bool BULK = STAGE == 1;     // the launch-bounds class
-    const size_t per_warp = (size_t)cap * NBUF * sizeof(int32_t) + 16;  // + two mbarriers
+    const size_t per_warp = (size_t)cap * NBUF * sizeof(int32_t) + 16 + (FUSED ? kFusedRingBytes : 0);  // + mbarriers
     auto kern = star_kernel<MODE, STAGE, FUSED, MAXLG>;
     // as many warps per SM as shared memory (228 KB, 1 KB of it reserved per CTA) and the register
     // budget of the launch bounds allow, in equal CTAs
@@ -790,6 +780,7 @@ static int launch_star(const StarParams &p, uint64_t nnz_hint, cudaStream_t st, 
     SHGO_REQUIRE(p.row_ptr && p.f && p.is_min, "null pointer");
     SHGO_REQUIRE((reinterpret_cast<uintptr_t>(p.col) & 3) == 0, "col must be 4-byte aligned");
     StarVariant v = star_variant();
+    if (FUSED) v.bulk = 2;  // the fused kernel's cp.async groups belong to the remote reads
     if (max_warps > 0 && (v.warps == 0 || max_warps < v.warps)) v.warps = max_warps;
 #define SHGO_STAR_CASE(S)                                                                      \
     if (v.bulk == S) {                                                                         \
@@ -797,8 +788,10 @@ static int launch_star(const StarParams &p, uint64_t nnz_hint, cudaStream_t st, 
         if (v.maxlg == 4) return launch_star_t<MODE, S, FUSED, 4>(p, nnz_hint, v.warps, st);   \
         return launch_star_t<MODE, S, FUSED, 3>(p, nnz_hint, v.warps, st);                     \
     }
-    SHGO_STAR_CASE(0)
-    SHGO_STAR_CASE(1)
+    if constexpr (!FUSED) {
+        SHGO_STAR_CASE(0)
+        SHGO_STAR_CASE(1)
+    }
     SHGO_STAR_CASE(2)
 #undef SHGO_STAR_CASE
     return fail(SHGO_B200_ERR_ARG, "SHGO_B200_STAR: unknown staging variant %d", v.bulk);
@@ -883,10 +876,7 @@ int shgo_b200_publish_ready(uint32_t *const *peer_flags, int npeers, int me, uin
 size_t shgo_b200_star_local_workspace(uint64_t rows)
 {
     // header + per-warp counts + per-warp id segments (each rounded up to whole tiles of 32 rows)
-    // + record segments (a quarter of the id capacity, 8 words each)
-    const size_t ids = rows + 32ull * kMaxStarWarps;
-    return align256((kCandHeader + (size_t)kMaxStarWarps + ids + 8 + (ids / 4 + kMaxStarWarps) * kRecWords) *
-                    sizeof(uint32_t));
+    return align256((kCandHeader + (size_t)kMaxStarWarps + rows + 32ull * kMaxStarWarps) * sizeof(uint32_t));
 }
 
 size_t shgo_b200_star_remote_workspace(uint64_t rows, uint64_t cand_cap)

@@ -4,19 +4,21 @@ SURVEY.md section 8(e): rank r of G owns Sobol indices / graph rows [r n/G, (r+1
 has a closed-form skip-ahead, so every shard generates and evaluates locally with no communication.
 The star test needs neighbours' f across shards.  Two exchanges are implemented:
 
-  'p2p'        the f shards are allocated with cudaMalloc, exported with CUDA IPC and
+  'p2p'        (default on GPUs) the f shards are allocated with cudaMalloc, exported with CUDA IPC and
                peer-mapped into every rank over NVLink.  Phase 1 classifies every row against its
                LOCAL neighbours (no communication); phase 2 finishes the few rows that survived --
                their remote neighbours' f values are read in place over NVLink by the kernel itself,
                8 bytes per remote neighbour of a candidate.  Collectives are used for plumbing only
                (one stream-ordered barrier per iteration, pool gather).
-  'fused'      (default on GPUs when remote neighbours sit at the row ends) the same data path in ONE
-               kernel: every rank publishes "my shard is written" into a flag word of every peer
-               right after its evaluation, and the star kernel reads the remote neighbours of its
-               candidates in place over NVLink as soon as the owner's flag is up -- issued at the
-               end of one tile, consumed at the end of the next, so the NVLink round trip hides
-               behind the local classification.  What was met before a peer was ready is finished by
-               the phase-2 kernel after the barrier, as in 'p2p'.
+  'fused'      (needs remote neighbours at the row ends) the same data path in ONE kernel: every rank
+               publishes "my shard is written" into a flag word of every peer right after its
+               evaluation, and the star kernel fetches the remote neighbours of its candidates in
+               place over NVLink as soon as the owner's flag is up -- cp.async straight into a ring in
+               shared memory, consumed three tiles later, so no register waits for the round trip.
+               What was met before a peer was ready is finished by the phase-2 kernel after the
+               barrier, as in 'p2p'.  Measured on 8 x B200 it is SLOWER than 'p2p' (DESIGN.md section 7:
+               the candidate bookkeeping costs the memory-bound local phase more than the hidden NVLink
+               time gives back), so it is an option, not the default.
   'allgather'  one all_gather of the f vector (NCCL on GPUs; gloo in the CPU tests), then the
                single-GPU star kernel on the rank's rows.  8 n (G-1)/G bytes received per GPU.
 
@@ -105,7 +107,7 @@ class ShardedSobolIteration:
     row_ptr[row0] (i.e. a slice of the global row_ptr), col_local the matching slice of col with
     GLOBAL vertex ids."""
 
-    def __init__(self, functor, gset, tab, n, row_ptr_local, col_local, group=None, exchange="fused",
+    def __init__(self, functor, gset, tab, n, row_ptr_local, col_local, group=None, exchange="p2p",
                  pool_cap=None, remote_at_ends=False, chunks=1, phase1_warps=0):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
