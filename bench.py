@@ -468,30 +468,17 @@ def main():
                           lb_h.ctypes.data, ub_h.ctypes.data, rp_h.data_ptr(), col_h.data_ptr(),
                           pool_h.data_ptr(), pool_h.numel(), ctypes.byref(cnt), ctypes.byref(nf), None)
         else:
-            # multi-GPU: same stages, host CSR shard uploaded every step, f exchanged over NCCL
-            rp_d = torch.empty(re_ + 1, dtype=torch.int64, device=dev)
-            col_dd = torch.empty(re_ * me, dtype=torch.int32, device=dev)
-            fe_all = torch.empty(ne, dtype=torch.float64, device=dev)
-            fe_my = fe_all[r0e:r0e + re_]
-            feas_e = torch.empty(re_, dtype=torch.uint8, device=dev)
-            ismin_e = torch.empty(re_, dtype=torch.uint8, device=dev)
-            work_e = hp.PoolWorkspace(re_, pool_h.numel(), dev)
-            cnt_h = torch.zeros(2, dtype=torch.int64).pin_memory()
+            # multi-GPU: the sharded C-ABI entry points (one ctx per rank, same peer-memory data path as
+            # `value`): host CSR shard uploaded over the rank's own PCIe link, pool indices read back
+            from shgo_b200.hostshard import ShardedHostIteration
+            shard = ShardedHostIteration(local, world, rank, re_)
+            # global offsets / ids, as the ABI wants them
+            rp_h = torch.arange(r0e * me, (r0e + re_ + 1) * me, me, dtype=torch.int64).pin_memory()
 
             def e2e_step():
-                rp_d.copy_(rp_h, non_blocking=True)
-                col_dd.copy_(col_h, non_blocking=True)
-                hp.eval_sobol(fid, F.G_NONE, tab, r0e, re_, f=fe_my, feasible=feas_e)
-                dist.all_gather_into_tensor(fe_all, fe_my)
-                # local row_ptr starts at 0: virtual bases so that row r0e maps to local row 0
-                _lib.call("shgo_b200_star_csr", rp_d.data_ptr() - r0e * 8, col_dd.data_ptr(),
-                          fe_all.data_ptr(), r0e, re_, re_ * me, ismin_e.data_ptr(), stream.cuda_stream)
-                hp.compact_pool(ismin_e, base=r0e, work=work_e)
-                cnt_h.copy_(work_e.count, non_blocking=True)
-                torch.cuda.synchronize()
-                c = min(int(cnt_h[0]), pool_h.numel())
-                pool_h[:c].copy_(work_e.idx[:c])
-                cnt.value = int(cnt_h[0])
+                shard.iterate(fid, F.G_NONE, D, BOUNDS, rp_h, col_h, remote_at_ends=True,
+                              pool_cap=pool_h.numel(), pool_out=pool_h)
+                cnt.value = shard.pool_count
 
         for _ in range(2):
             e2e_step()
@@ -512,10 +499,12 @@ def main():
                "d2h_bytes_per_step": d2h * world, "points": ne, "ms_per_step": wall * 1e3,
                "note": "host CSR (pinned) uploaded, pool indices read back, every step; "
                        + ("C-ABI shgo_b200_iterate_sobol_host" if world == 1 else
-                          "every rank uploads its CSR shard over its own PCIe link, f exchanged with "
-                          "an NCCL all_gather")}
+                          "C-ABI shgo_b200_iterate_sobol_host_shard_begin / _finish, one ctx per rank: every "
+                          "rank uploads its CSR shard over its own PCIe link, f stays in peer-mapped shards")}
         if world == 1:
             _lib.lib().shgo_b200_ctx_destroy(ctx)
+        else:
+            shard.close()
 
     it.close()
     if rank != 0:

@@ -356,6 +356,34 @@ SHGO_B200_API int shgo_b200_iterate_sobol_host(shgo_b200_ctx *ctx, int functor, 
                                  uint64_t pool_cap, uint64_t *pool_count /*[host]*/,
                                  uint64_t *nfev /*[host]*/, double *f_out /*[host] n or NULL*/);
 
+/* Sharded form of the host-buffer path (one ctx per rank / GPU): GPU r of nshards owns Sobol indices
+ * and graph rows [r * rows_per_shard, (r+1) * rows_per_shard) and holds its shard of f in two
+ * cudaMalloc'ed buffers (used alternately, so one barrier per iteration suffices) that every peer maps
+ * over NVLink with CUDA IPC -- the same data path as the device-resident multi-GPU step.
+ *   1. _shard_init     allocates the f buffers, returns their two 64-byte IPC handles
+ *   2. the caller exchanges the handles of all ranks (MPI_Allgather, torch.distributed, ...)
+ *   3. _shard_connect  maps the peers' buffers: all_handles = [nshards][2][64]
+ *   per iteration:
+ *   4. _shard_begin    uploads the rank's CSR rows (row_ptr: rows_per_shard + 1 GLOBAL offsets, col: the
+ *                      matching slice with GLOBAL vertex ids), evaluates its Sobol shard, enqueues phase 1
+ *                      of the star test; returns once the rank's shard of f is complete
+ *   5. the caller's BARRIER ("every shard of f is written")
+ *   6. _shard_finish   phase 2 (remote neighbours of the candidates, read in place over NVLink), pool
+ *                      compaction, read-back: pool_idx are global vertex ids of this rank's rows
+ * Replaces the same reference code as shgo_b200_iterate_sobol_host. */
+SHGO_B200_API int shgo_b200_ctx_shard_init(shgo_b200_ctx *ctx, int nshards, int my_shard,
+                             uint64_t rows_per_shard, unsigned char *handles_out /*[host] [2][64]*/);
+SHGO_B200_API int shgo_b200_ctx_shard_connect(shgo_b200_ctx *ctx,
+                                const unsigned char *all_handles /*[host] [nshards][2][64]*/);
+SHGO_B200_API int shgo_b200_iterate_sobol_host_shard_begin(shgo_b200_ctx *ctx, int functor, int gset, int d,
+                                             const uint32_t *sv /*[host]*/, const double *lb /*[host]*/,
+                                             const double *ub /*[host]*/,
+                                             const int64_t *row_ptr /*[host] rows_per_shard+1*/,
+                                             const int32_t *col /*[host]*/, int remote_at_ends);
+SHGO_B200_API int shgo_b200_iterate_sobol_host_shard_finish(shgo_b200_ctx *ctx, int64_t *pool_idx /*[host]*/,
+                                              uint64_t pool_cap, uint64_t *pool_count /*[host]*/,
+                                              uint64_t *nfev /*[host]*/);
+
 /* ---- measurement helper ------------------------------------------------------------------------------
  * Dependent-chain-free DFMA loop; *flops = FP64 flops performed.  Used by bench.py to measure the
  * FP64 pipe peak on the box (no published number is trusted). */

@@ -64,6 +64,10 @@ SIGNATURES = {
     "shgo_b200_ctx_destroy": (None, [_vp]),
     "shgo_b200_iterate_sobol_host": (_i, [_vp, _i, _i, _i, _u64, _u64, _vp, _vp, _vp, _vp, _vp,
                                           _vp, _u64, _vp, _vp, _vp]),
+    "shgo_b200_ctx_shard_init": (_i, [_vp, _i, _i, _u64, _vp]),
+    "shgo_b200_ctx_shard_connect": (_i, [_vp, _vp]),
+    "shgo_b200_iterate_sobol_host_shard_begin": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "shgo_b200_iterate_sobol_host_shard_finish": (_i, [_vp, _vp, _u64, _vp, _vp]),
     "shgo_b200_fp64_peak": (_i, [_i, _vp, _vp, _vp]),
 }
 

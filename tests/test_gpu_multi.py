@@ -38,3 +38,12 @@ def test_sharded_lattice_generation_matches_single_gpu(nproc):
         pytest.skip("needs %d GPUs" % nproc)
     r = _torchrun(nproc, "check_sharded_lattice.py", port=29541 + nproc)
     assert r.returncode == 0 and "MISMATCH" not in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_sharded_host_buffer_entry_points_match_single_gpu(nproc):
+    """the C-ABI host-buffer path, one ctx per rank, against shgo_b200_iterate_sobol_host on one GPU"""
+    if _gpus() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    r = _torchrun(nproc, "check_sharded_host.py", "20", port=29551 + nproc)
+    assert r.returncode == 0 and ": OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
