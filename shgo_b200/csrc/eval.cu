@@ -102,7 +102,7 @@ __device__ __forceinline__ void eval_tiles(Src &src, uint64_t ntiles, int d, dou
 }
 
 template <class F, template <int> class SrcT, bool PUSH>
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kEvalThreads, F::kMinBlocks)
 eval_kernel(typename SrcT<F::P>::Params sp, int d, double *__restrict__ f,
             uint8_t *__restrict__ feasible, const Replicas rep)
 {

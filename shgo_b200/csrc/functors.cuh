@@ -87,6 +87,7 @@ constexpr double kE = 2.718281828459045;      // np.e
 // scipy.optimize.rosen:  sum(100.0*(x[1:]-x[:-1]**2.0)**2.0 + (1-x[:-1])**2.0, axis=0)
 struct Rosenbrock {
     static constexpr int P = 4;
+    static constexpr int kMinBlocks = 1;  // resident CTAs per SM the register budget must allow
     static bool dim_ok(int d) { return d >= 2; }
     template <class Src>
     static __device__ __forceinline__ void run(Src &src, int d, double (&f)[P], uint32_t &feas)
@@ -112,6 +113,7 @@ struct Rosenbrock {
 // 10*len(x) + np.sum(x**2 - 10*np.cos(2*np.pi*x))
 struct Rastrigin {
     static constexpr int P = 4;
+    static constexpr int kMinBlocks = 3;  // resident CTAs per SM the register budget must allow
     static bool dim_ok(int d) { return d >= 1; }
     template <class Src>
     static __device__ __forceinline__ void run(Src &src, int d, double (&f)[P], uint32_t &feas)
@@ -134,6 +136,7 @@ struct Rastrigin {
 // -20*np.exp(-0.2*np.sqrt(np.sum(x**2)/d)) - np.exp(np.sum(np.cos(2*np.pi*x))/d) + 20 + np.e
 struct Ackley {
     static constexpr int P = 2;
+    static constexpr int kMinBlocks = 3;  // resident CTAs per SM the register budget must allow
     static bool dim_ok(int d) { return d >= 1; }
     template <class Src>
     static __device__ __forceinline__ void run(Src &src, int d, double (&f)[P], uint32_t &feas)
@@ -164,6 +167,7 @@ struct Ackley {
 // restatement of the same chain.
 struct StyblinskiTang {
     static constexpr int P = 8;
+    static constexpr int kMinBlocks = 1;  // resident CTAs per SM the register budget must allow
     static bool dim_ok(int d) { return d >= 1; }
     template <class Src>
     static __device__ __forceinline__ void run(Src &src, int d, double (&f)[P], uint32_t &feas)
@@ -188,6 +192,7 @@ struct StyblinskiTang {
 // reference _shgo.py:329-333
 struct Eggholder {
     static constexpr int P = 2;
+    static constexpr int kMinBlocks = 3;  // resident CTAs per SM the register budget must allow
     static bool dim_ok(int d) { return d == 2; }
     template <class Src>
     static __device__ __forceinline__ void run(Src &src, int, double (&f)[P], uint32_t &feas)
@@ -210,6 +215,7 @@ struct Eggholder {
 template <bool CONS>
 struct CattleFeed {
     static constexpr int P = 4;
+    static constexpr int kMinBlocks = 1;
     static bool dim_ok(int d) { return d == 4; }
     template <class Src>
     static __device__ __forceinline__ void run(Src &src, int, double (&f)[P], uint32_t &feas)
@@ -253,6 +259,7 @@ struct CattleFeed {
 template <bool CONS>
 struct Sphere {
     static constexpr int P = 4;
+    static constexpr int kMinBlocks = 1;
     static bool dim_ok(int d) { return d >= 1 && (!CONS || d < 8); }
     template <class Src>
     static __device__ __forceinline__ void run(Src &src, int d, double (&f)[P], uint32_t &feas)
