@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cpu-log2n", type=int, default=None, help="override the CPU sample size (default: --e2e-log2n)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "fused", "allgather"],
                     help="how neighbour f values cross GPUs (N > 1)")
+    ap.add_argument("--no-filter", action="store_true", help="p2p exchange without the block-minimum filter")
     ap.add_argument("--chunks", type=int, default=1, help="p2p exchange: classify the shard in chunks (overlap)")
     ap.add_argument("--phase1-warps", type=int, default=0, help="p2p + chunks: resident warps per SM of phase 1")
     ap.add_argument("--workload", default="cfg5", choices=["cfg5", "delaunay"],
@@ -367,7 +368,7 @@ def main():
     # are the last entries of every row: the remote_at_ends promise of the sharded star test holds
     it = sdist.ShardedSobolIteration(fid, F.G_NONE, tab, n, row_ptr_l, col_l, exchange=args.exchange,
                                      pool_cap=rows // 8, remote_at_ends=True, chunks=args.chunks,
-                                     phase1_warps=args.phase1_warps)
+                                     phase1_warps=args.phase1_warps, filter_remote=not args.no_filter)
     stream = torch.cuda.current_stream()
 
     def step(ev=None):

@@ -36,11 +36,16 @@ SIGNATURES = {
     "shgo_b200_star_local_workspace": (_sz, [_u64]),
     "shgo_b200_star_remote_workspace": (_sz, [_u64, _u64]),
     "shgo_b200_star_csr_remote": (_i, [_vp, _vp, _vp, _vp, _i, _u64, _i, _u64, _u64, _i, _vp, _vp, _u64, _vp, _sz, _vp]),
+    "shgo_b200_star_csr_remote_filtered": (_i, [_vp, _vp, _vp, _vp, _i, _u64, _i, _u64, _u64, _i, _vp, _vp, _u64, _vp,
+                                                _sz, _vp, _i, _vp]),
+    "shgo_b200_blockmin_layout": (_i, [_i, _i]),
+    "shgo_b200_eval_sobol_blockmin": (_i, [_i, _i, _i, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "shgo_b200_star_csr_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _u64, _i, _u64, _u64, _u64, _vp, ctypes.c_uint32,
                                       _vp, _vp, _sz, _vp, _vp]),
     "shgo_b200_publish_ready": (_i, [_vp, _i, _i, ctypes.c_uint32, _vp]),
     "shgo_b200_ipc_alloc": (_i, [_sz, _vp, _vp]),
     "shgo_b200_ipc_open": (_i, [_vp, _vp]),
+    "shgo_b200_copy_async": (_i, [_vp, _vp, _sz, _vp]),
     "shgo_b200_ipc_close": (_i, [_vp]),
     "shgo_b200_ipc_free": (_i, [_vp]),
     "shgo_b200_compact_workspace": (_sz, [_u64]),

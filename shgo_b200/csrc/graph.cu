@@ -507,6 +507,14 @@ int shgo_b200_ipc_open(const unsigned char *handle64, void **ptr)
     return SHGO_B200_OK;
 }
 
+int shgo_b200_copy_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (bytes == 0) return SHGO_B200_OK;
+    SHGO_REQUIRE(dst && src, "null pointer");
+    SHGO_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, as_stream(stream)));
+    return SHGO_B200_OK;
+}
+
 int shgo_b200_ipc_close(void *ptr)
 {
     if (ptr) SHGO_CUDA_TRY(cudaIpcCloseMemHandle(ptr));

@@ -573,6 +573,19 @@ star_kernel(const StarParams p)
 struct ShardedF {
     const double *const *shards;  // device array of nshards base pointers (own shard = local HBM)
     uint32_t rows_per_shard;
+    // optional conservative filter: block_min[w >> 5] = min of f over the 32 vertices around w, for
+    // ALL shards, in LOCAL memory (gathered in bulk while phase 1 runs).  fv < block_min proves
+    // fv < f[w] without the 8-byte read over NVLink; a candidate is the minimum of its ~25 local
+    // neighbours, so it also undercuts the minimum of 32 unrelated values about 45 % of the time.
+    const double *block_min;
+    int plog;  // log2 of the evaluation kernel's points per thread: fixes which 32 vertices form a group
+    __device__ __forceinline__ bool needs_read(double fv, int32_t w) const
+    {
+        if (block_min == nullptr) return true;
+        const uint32_t u = (uint32_t)w, tl = 8 + plog;
+        const uint32_t g = ((u >> tl) << (tl - 5)) + ((u & 255u) >> (5 - plog));
+        return !(fv < __ldg(block_min + g));
+    }
     __device__ __forceinline__ double operator()(int32_t w) const
     {
         const uint32_t q = (uint32_t)w / rows_per_shard;
@@ -621,6 +634,8 @@ __device__ __forceinline__ void star_remote_one(uint64_t lr, const int64_t *__re
                 all_hi = all_hi && (use[4 + u] || u >= nhi);
             }
 #pragma unroll
+            for (int u = 0; u < 8; ++u) use[u] = use[u] && facc.needs_read(fv, w[u]);
+#pragma unroll
             for (int u = 0; u < 8; ++u) fn[u] = use[u] ? facc(w[u]) : pos_inf();
 #pragma unroll
             for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
@@ -637,7 +652,8 @@ __device__ __forceinline__ void star_remote_one(uint64_t lr, const int64_t *__re
 #pragma unroll
             for (int u = 0; u < 8; ++u) w[u] = __ldg(col + (k + u < e ? k + u : e - 1));
 #pragma unroll
-            for (int u = 0; u < 8; ++u) fn[u] = ((uint32_t)w[u] - o0 < on) ? pos_inf() : facc(w[u]);
+            for (int u = 0; u < 8; ++u)
+                fn[u] = ((uint32_t)w[u] - o0 < on || !facc.needs_read(fv, w[u])) ? pos_inf() : facc(w[u]);
 #pragma unroll
             for (int u = 0; u < 8; ++u) ok = ok && (fv < fn[u]);
         }
@@ -890,6 +906,19 @@ int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const 
                               const void *cand_ws, uint64_t cand_cap, void *tmp, size_t tmp_bytes,
                               void *stream)
 {
+    return shgo_b200_star_csr_remote_filtered(row_ptr, col, f_shards, f_own, nshards, rows_per_shard, my_shard,
+                                              row0, rows, remote_at_ends, flags, cand_ws, cand_cap, tmp,
+                                              tmp_bytes, nullptr, 0, stream);
+}
+
+int shgo_b200_star_csr_remote_filtered(const int64_t *row_ptr, const int32_t *col,
+                                       const double *const *f_shards, const double *f_own, int nshards,
+                                       uint64_t rows_per_shard, int my_shard, uint64_t row0, uint64_t rows,
+                                       int remote_at_ends, uint8_t *flags, const void *cand_ws,
+                                       uint64_t cand_cap, void *tmp, size_t tmp_bytes,
+                                       const double *block_min, int layout_plog, void *stream)
+{
+    SHGO_REQUIRE(block_min == nullptr || (layout_plog >= 0 && layout_plog <= 5), "bad group layout");
     cudaStream_t st = as_stream(stream);
     if (rows == 0) return SHGO_B200_OK;
     SHGO_REQUIRE(row_ptr && f_shards && f_own && flags && (tmp || cand_ws), "null pointer");
@@ -898,7 +927,7 @@ int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const 
     const uint64_t own0 = (uint64_t)my_shard * rows_per_shard;
     SHGO_REQUIRE(row0 >= own0 && row0 + rows <= own0 + rows_per_shard, "classified rows outside the owned shard");
     if (cand_ws) {  // phase 1 already listed the candidates
-        ShardedF fa{f_shards, (uint32_t)rows_per_shard};
+        ShardedF fa{f_shards, (uint32_t)rows_per_shard, block_min, layout_plog};
         star_remote_seg_kernel<<<sm_count() * 8, 256, 0, st>>>(static_cast<const uint32_t *>(cand_ws), row_ptr, col,
                                                              fa, f_own, own0, rows_per_shard, row0,
                                                              remote_at_ends, flags);
@@ -915,7 +944,7 @@ int shgo_b200_star_csr_remote(const int64_t *row_ptr, const int32_t *col, const 
     p += shgo_b200_compact_workspace(rows);
     uint64_t *ncand = reinterpret_cast<uint64_t *>(p);
     if (int rc = compact_flags(flags, rows, /*match=*/2, 0, cand, cand_cap, ncand, ctmp, st)) return rc;
-    ShardedF facc{f_shards, (uint32_t)rows_per_shard};
+    ShardedF facc{f_shards, (uint32_t)rows_per_shard, block_min, layout_plog};
     // candidates beyond cand_cap would be left with flag 2; callers size cand_cap = rows to be safe
     uint64_t blocks = (rows / 16 + 255) / 256;  // ~ one thread per expected candidate, capped
     const uint64_t capb = (uint64_t)sm_count() * 8;

@@ -108,7 +108,7 @@ class ShardedSobolIteration:
     GLOBAL vertex ids."""
 
     def __init__(self, functor, gset, tab, n, row_ptr_local, col_local, group=None, exchange="p2p",
-                 pool_cap=None, remote_at_ends=False, chunks=1, phase1_warps=0):
+                 pool_cap=None, remote_at_ends=False, chunks=1, phase1_warps=0, filter_remote=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -146,6 +146,17 @@ class ShardedSobolIteration:
             self._cand_ws = torch.empty(_lib.lib().shgo_b200_star_local_workspace(self.rows), dtype=torch.uint8,
                                         device=dev)
             self._comm = torch.cuda.Stream(device=dev)
+            # Conservative filter of the remote phase: every rank also produces the minimum of each
+            # 32 consecutive f values (1/32 of f) and PUSHES that small vector into every peer's
+            # copy with copy-engine transfers while phase 1 runs; a candidate whose f is below the
+            # block minimum of a remote neighbour needs no 8-byte NVLink read for it (about 45 % of
+            # them).  Two alternating sets of copies, like f.
+            self.filter_remote = (bool(filter_remote) and self.exchange == "p2p" and self.rows % 32 == 0
+                                  and self.world > 1)
+            self._plog = hp.blockmin_layout(functor, gset)
+            self.filter_remote = self.filter_remote and self._plog >= 0 and self.rows % (256 << self._plog) == 0
+            if self.filter_remote:
+                self._bmin = [PeerMappedVector(n // 32, group), PeerMappedVector(n // 32, group)]
             # 'p2p' with chunks > 1: the rows are classified in chunks; phase 2 of chunk c (bound by the
             # rate of small NVLink reads) runs on a second stream underneath phase 1 of chunk c+1
             # (bound by HBM), which keeps at most `phase1_warps` warps per SM resident so that the
@@ -188,9 +199,26 @@ class ShardedSobolIteration:
             self.peer = self.peers[self._k & 1]
             self.f_my = self.peer.local
             self._k += 1
-        hp.eval_sobol(self.functor, self.gset, self.tab, self.row0, self.rows, f=self.f_my, feasible=self.feas)
+        bmin = None
+        if self.peer is not None and getattr(self, "filter_remote", False):
+            bm = self._bmin[(self._k - 1) & 1]
+            lo, cnt = self.row0 // 32, self.rows // 32
+            bmin = bm.local
+            hp.eval_sobol_blockmin(self.functor, self.gset, self.tab, self.row0, self.rows, self.f_my, self.feas,
+                                   bm.local)
+        else:
+            hp.eval_sobol(self.functor, self.gset, self.tab, self.row0, self.rows, f=self.f_my, feasible=self.feas)
         if events:
             events[0].record()
+        if bmin is not None:
+            # push this rank's block minima into every peer's copy (copy engines, side stream); the
+            # barrier that follows on the same stream then also covers them
+            self._comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm):
+                src = bm.own_ptr + lo * 8
+                for q, base in enumerate(bm.peer_ptrs):
+                    if q != self.rank:
+                        _lib.call("shgo_b200_copy_async", base + lo * 8, src, cnt * 8, self._comm.cuda_stream)
         if self.exchange == "fused":
             # tell every peer that this shard is written, then classify: candidates read their
             # remote neighbours in place inside the kernel once the owner's word is up.  The barrier
@@ -230,7 +258,8 @@ class ShardedSobolIteration:
             self._barrier_wait()
             hp.star_csr_remote(self.row_ptr, self.col, self.row0, self.peer.table, self.peer.own_ptr, self.world,
                                self.rows, self.rank, self.is_min, self._remote_tmp, self.off0,
-                               remote_at_ends=self.remote_at_ends, cand_ws=self._cand_ws)
+                               remote_at_ends=self.remote_at_ends, cand_ws=self._cand_ws, block_min=bmin,
+                               layout_plog=getattr(self, "_plog", 0))
         else:
             if self.exchange == "allgather":
                 _all_gather(self.f_all, self.f_my, self.group)
@@ -270,6 +299,9 @@ class ShardedSobolIteration:
                 p.close()
             if self.exchange == "fused":
                 self._ready.close()
+            if getattr(self, "filter_remote", False):
+                for b in self._bmin:
+                    b.close()
             self.peer = None
             self.peers = []
 

@@ -111,6 +111,26 @@ def eval_sobol(functor, gset, tab, k0, n, f=None, feasible=None, want_feasible=T
     return f, feasible
 
 
+def blockmin_layout(functor, gset):
+    """log2 of the evaluation kernel's points per thread (fixes which 32 vertices form a group of the
+    remote-phase filter, see include/shgo_b200.h), -1 for an unregistered pair"""
+    return _lib.lib().shgo_b200_blockmin_layout(functor, gset)
+
+
+def blockmin_group(i, plog):
+    """group index of vertex / output index i (int or tensor) in the block_min vector"""
+    tl = 8 + plog
+    return ((i >> tl) << (tl - 5)) + ((i & 255) >> (5 - plog))
+
+
+def eval_sobol_blockmin(functor, gset, tab, k0, n, f, feasible, block_min):
+    """eval_sobol that also fills block_min (the whole n_total / 32 vector) with the group minima of
+    its outputs (the filter of the sharded star test's remote phase); k0, n multiples of the tile."""
+    _lib.call("shgo_b200_eval_sobol_blockmin", functor, gset, tab.d, k0, n, _ptr(tab.sv), _ptr(tab.lb),
+              _ptr(tab.ub), _ptr(f), _ptr(feasible), _ptr(block_min), _stream())
+    return f, feasible
+
+
 def eval_points(functor, gset, x_soa, f=None, feasible=None):
     """Evaluate a registered functor on caller-supplied points, x_soa = (d, n) float64."""
     assert x_soa.dtype == torch.float64 and x_soa.dim() == 2
@@ -307,7 +327,7 @@ def star_csr_local(row_ptr_local, col_local, own0, f_own, feasible, flags, nfev,
 
 def star_csr_remote(row_ptr_local, col_local, own0, peer_table, f_own_ptr, nshards, rows_per_shard,
                     my_shard, flags, tmp, off0=None, r0=None, nrows=None, remote_at_ends=False,
-                    cand_ws=None):
+                    cand_ws=None, block_min=None, layout_plog=0):
     """Multi-GPU phase 2: candidates' remote neighbours, f read in place from the peer-mapped shards.
     remote_at_ends: promise that remote neighbours form a prefix/suffix of every row (true for
     ascending rows); enables the two-ends lookup."""
@@ -316,10 +336,11 @@ def star_csr_remote(row_ptr_local, col_local, own0, peer_table, f_own_ptr, nshar
         off0 = int(row_ptr_local[0].item())
     r0 = own0 if r0 is None else r0
     nrows = own_rows if nrows is None else nrows
-    _lib.call("shgo_b200_star_csr_remote", row_ptr_local.data_ptr() - own0 * 8,
+    # block_min: the gathered block minima of ALL shards (float64 [n / 32]): remote reads it rules out are skipped
+    _lib.call("shgo_b200_star_csr_remote_filtered", row_ptr_local.data_ptr() - own0 * 8,
               col_local.data_ptr() - off0 * 4, _ptr(peer_table), f_own_ptr, nshards, rows_per_shard,
               my_shard, r0, nrows, 1 if remote_at_ends else 0, flags.data_ptr() + (r0 - own0), _ptr(cand_ws),
-              nrows, _ptr(tmp), tmp.numel() if tmp is not None else 0, _stream())
+              nrows, _ptr(tmp), tmp.numel() if tmp is not None else 0, _ptr(block_min), layout_plog, _stream())
     return flags
 
 

@@ -131,6 +131,20 @@ def shgo_b200_star_csr_remote(row_ptr, col, f_shards, f_own, nshards, rows_per_s
     _req(row0 >= own0 and row0 + rows <= own0 + rows_per_shard, "classified rows outside the owned shard")
 
 
+def shgo_b200_star_csr_remote_filtered(row_ptr, col, f_shards, f_own, nshards, rows_per_shard, my_shard, row0, rows,
+                                       ends, flags, cand_ws, cand_cap, tmp, tmp_bytes, block_min, plog, stream):
+    _req(not block_min or 0 <= plog <= 5, "bad group layout")
+    shgo_b200_star_csr_remote(row_ptr, col, f_shards, f_own, nshards, rows_per_shard, my_shard, row0, rows, ends,
+                              flags, cand_ws, cand_cap, tmp, tmp_bytes, stream)
+
+
+def shgo_b200_eval_sobol_blockmin(functor, gset, d, k0, n, sv, lb, ub, f, feasible, block_min, stream):
+    _sobol_tables(sv, d, k0, n, lb, ub)
+    if n == 0:
+        return
+    _req(f and block_min, "null output")
+
+
 def shgo_b200_star_csr_fused(row_ptr, col, f_shards, f_own, feasible, nshards, rows_per_shard, my_shard, row0, rows,
                              nnz_hint, ready, epoch, flags, cand_ws, cand_ws_bytes, nfev, stream):
     _req(f_shards and f_own and ready and cand_ws, "null pointer")

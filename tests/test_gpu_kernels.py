@@ -196,6 +196,32 @@ def test_transcendental_functors_near_their_minimum(hp, functor, d, width):
     _close(f.cpu().numpy(), orc.eval_points(functor, None, pts)[0], functor, pts)
 
 
+def test_eval_sobol_block_minima(hp):
+    """group minima of the outputs (+inf for infeasible / NaN) in the layout of include/shgo_b200.h"""
+    for fname, gname, bounds in (("cattle_feed", "cattle_feed", [(0.0, 1.0)] * 4), ("styblinski_tang", None, [(-5.0, 5.0)] * 8),
+                                 ("ackley", None, [(-32.768, 32.768)] * 3)):
+        fid, gid = orc.FUNCTOR_IDS[fname], orc.GSET_IDS[gname]
+        plog = hp.blockmin_layout(fid, gid)
+        tile = 256 << plog
+        tab = hp.SobolTables(bounds)
+        ntot = 8 * tile
+        bm = torch.full((ntot // 32,), -7.0, dtype=torch.float64, device="cuda")
+        for k0, n in ((0, 3 * tile), (3 * tile, 5 * tile)):
+            f = torch.empty(n, dtype=torch.float64, device="cuda")
+            feas = torch.empty(n, dtype=torch.uint8, device="cuda")
+            hp.eval_sobol_blockmin(fid, gid, tab, k0, n, f, feas, bm)
+            f2, feas2 = hp.eval_sobol(fid, gid, tab, k0, n)
+            assert torch.equal(f, f2) and torch.equal(feas, feas2)
+        fall, _ = hp.eval_sobol(fid, gid, tab, 0, ntot)
+        ref = np.full(ntot // 32, np.inf)
+        np.minimum.at(ref, hp.blockmin_group(np.arange(ntot), plog), fall.cpu().numpy())
+        assert np.array_equal(bm.cpu().numpy(), ref), fname
+        from shgo_b200 import _lib
+        with pytest.raises(_lib.Shgob200Error):
+            hp.eval_sobol_blockmin(fid, gid, tab, 32, tile, f, feas, bm)
+    assert hp.blockmin_layout(1, 1) == -1
+
+
 def test_mask_infeasible(hp):
     n = 10000
     rng = np.random.default_rng(3)
@@ -511,6 +537,22 @@ def test_two_phase_sharded_star_emulated_on_one_gpu(hp, nshards):
             hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, fl4, None,
                                remote_at_ends=True, cand_ws=cws)
             assert torch.equal(fl4, flags)
+            # phase 2 with the conservative block-minimum filter: same flags, fewer remote reads
+            plog = 2
+            grp = hp.blockmin_group(np.arange(n), plog)
+            bm_h = np.full(n // 32, np.inf)
+            np.minimum.at(bm_h, grp, np.where(np.isnan(f_h), np.inf, f_h))
+            bmin = torch.from_numpy(bm_h).cuda()
+            fl6 = torch.empty_like(flags)
+            hp.star_csr_local(rp_l, col_l, row0, f_sh[s], None, fl6, nfev, cand_ws=cws, remote_at_ends=True)
+            hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, fl6, None,
+                               remote_at_ends=True, cand_ws=cws, block_min=bmin, layout_plog=plog)
+            assert torch.equal(fl6, flags)
+            fl7 = torch.empty_like(flags)
+            hp.star_csr_local(rp_l, col_l, row0, f_sh[s], None, fl7, nfev)
+            hp.star_csr_remote(rp_l, col_l, row0, table, f_sh[s].data_ptr(), nshards, rows, s, fl7, tmp,
+                               block_min=bmin, layout_plog=plog)
+            assert torch.equal(fl7, flags)
             # phases 1 + 2 fused in one kernel: peers all ready / none ready / some ready
             for ready_mask in (None, 0, 0b10101010):
                 epoch = 7

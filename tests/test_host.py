@@ -242,7 +242,7 @@ def test_abi_contract_rejects_what_the_library_rejects():
     # every compute symbol the product marshals has a contract
     from shgo_b200 import _lib
     skip = ("version", "last_error", "device_info", "workspace", "ipc_", "ctx_", "fp64_peak",
-            "iterate_sobol", "lattice_star")
+            "iterate_sobol", "lattice_star", "blockmin_layout", "copy_async")
     for name in _lib.SIGNATURES:
         if not any(k in name for k in skip) or name == "shgo_b200_lattice_star_part":
             assert hasattr(A, name), name

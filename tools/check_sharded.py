@@ -29,9 +29,11 @@ rp_l = torch.arange(row0 * m, (row0 + rows + 1) * m, m, dtype=torch.int64, devic
 i = torch.arange(row0, row0 + rows, dtype=torch.int32, device=dev)[:, None]
 col_l = (i ^ (1 << torch.arange(m, dtype=torch.int32, device=dev))[None, :]).reshape(-1)
 res = {}
-for ex in ("fused", "p2p", "allgather", "p2p-walk"):
+for ex in ("fused", "p2p", "allgather", "p2p-walk", "p2p-nofilter"):
     it = sd.ShardedSobolIteration(F.F_RASTRIGIN, F.G_NONE, tab, n, rp_l, col_l, exchange=ex.split("-")[0],
-                                  remote_at_ends=(ex in ("p2p", "fused")))
+                                  remote_at_ends=(ex in ("p2p", "fused", "p2p-nofilter")),
+                                  filter_remote=(ex != "p2p-nofilter"))
+    assert it.filter_remote == (ex in ("p2p", "p2p-walk")) if hasattr(it, "filter_remote") else True
     assert it.exchange == ex.split("-")[0]
     for _ in range(3):
         it.step()
@@ -41,6 +43,7 @@ for ex in ("fused", "p2p", "allgather", "p2p-walk"):
 ok = np.array_equal(res["p2p"][0], res["allgather"][0]) and res["p2p"][1] == res["allgather"][1]
 ok = ok and np.array_equal(res["p2p"][0], res["p2p-walk"][0])
 ok = ok and np.array_equal(res["p2p"][0], res["fused"][0]) and res["p2p"][1] == res["fused"][1]
+ok = ok and np.array_equal(res["p2p"][0], res["p2p-nofilter"][0]) and res["p2p"][1] == res["p2p-nofilter"][1]
 if rank == 0:
     rp, col = hp.hypercube_csr(n, dev)
     f, feas = hp.eval_sobol(F.F_RASTRIGIN, F.G_NONE, tab, 0, n)
