@@ -114,6 +114,16 @@ SHGO_B200_API int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_
                                  int64_t *row_ptr, int32_t *col, uint64_t col_cap, uint64_t *nnz,
                                  void *tmp, size_t tmp_bytes, void *stream);
 
+/* Every undirected edge {a, b} of a symmetric CSR once, as the degenerate simplex [a, b, b] (a < b, any
+ * order): feeding them to the next shgo_b200_csr_from_simplices call together with the new simplices
+ * gives the union of the triangulations -- the reference's connect() only ever adds edges
+ * (_vertex.py:116-131), so a second vf_to_vv call merges into the first.  out: [cap][3], *count edges
+ * found (nnz / 2).  shgo_b200_row_present: present[r] = 1 iff row r is non-empty, i.e. the vertex exists in
+ * the reference's cache (_vertex.py:304-317). */
+SHGO_B200_API int shgo_b200_csr_edges3(const int64_t *row_ptr, const int32_t *col, uint64_t n, int32_t *out,
+                         uint64_t cap, uint64_t *count, void *stream);
+SHGO_B200_API int shgo_b200_row_present(const int64_t *row_ptr, uint64_t n, uint8_t *present, void *stream);
+
 /* Position (3*s + slot) at which vf_to_vv first touches each vertex while it walks the simplices
  * (reference _complex.py:1064-1069), ~0 for vertices it never touches.  This is the insertion
  * order of the reference's vertex cache (_vertex.py:304-317), i.e. the order in which

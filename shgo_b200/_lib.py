@@ -22,6 +22,8 @@ SIGNATURES = {
     "shgo_b200_mask_infeasible": (_i, [_vp, _u64, _vp, _i, _vp, _vp]),
     "shgo_b200_csr_workspace": (_sz, [_u64, _i, _u64]),
     "shgo_b200_csr_from_simplices": (_i, [_vp, _u64, _i, _u64, _vp, _vp, _u64, _vp, _vp, _sz, _vp]),
+    "shgo_b200_csr_edges3": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "shgo_b200_row_present": (_i, [_vp, _u64, _vp, _vp]),
     "shgo_b200_first_seen": (_i, [_vp, _u64, _i, _u64, _vp, _vp]),
     "shgo_b200_morton_workspace": (_sz, [_u64]),
     "shgo_b200_morton_order": (_i, [_vp, _u64, _i, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -383,13 +383,9 @@ class DeviceComplex:
         self._mesh_calls += 1
         if self._row_ptr is not None and self._n > 0:
             # carry the edges of earlier triangulations over as degenerate [a, b, b] triples
-            rp, col = self._row_ptr, self._col
-            rows = torch.repeat_interleave(torch.arange(self._n, device=self.device, dtype=torch.int32),
-                                           (rp[1:] - rp[:-1]).to(torch.int64))
-            keep = rows < col
-            old = torch.stack([rows[keep], col[keep], col[keep]], 1)
-            new = simp_d[:, :3] if simp_d.shape[1] >= 3 else torch.cat([simp_d, simp_d[:, 1:2]], 1)
-            simp_d = torch.cat([old, new.to(torch.int32)], 0).contiguous()
+            old = hp.csr_edges3(self._row_ptr, self._col)
+            new = hp.relabel3(simp_d, n)                      # first three slots, same numbering
+            simp_d = torch.cat([old, new], 0)
         self._row_ptr, self._col = hp.csr_from_simplices(simp_d, n)
         self._row_ptr_host = self._col_host = None
         self._points_host = pts
@@ -483,7 +479,7 @@ class DeviceComplex:
             nf = torch.zeros(1, dtype=torch.int64, device=self.device)
             self._is_min = hp.star_csr(self._row_ptr, self._col, self._f, feasible=self._feas, nfev=nf)
         self.V.nfev = int(nf.item())
-        present = (self._row_ptr[1:] > self._row_ptr[:-1]).to(torch.uint8)
+        present = hp.row_present(self._row_ptr)
         if self.mode == "hostgraph":
             # every vertex the generator created exists, also one without edges yet: it is
             # trivially a minimiser (all([]) is True, _vertex.py:148) and counts towards nfev;

@@ -264,6 +264,25 @@ def scatter_u8(src, idx, out):
     return out
 
 
+def csr_edges3(row_ptr, col):
+    """(nnz / 2, 3) int32: every undirected edge of a symmetric CSR once, as a degenerate simplex
+    [a, b, b]; together with new simplices they give csr_from_simplices the union of the meshes."""
+    n = row_ptr.numel() - 1
+    cap = col.numel() // 2
+    out = torch.empty((max(cap, 1), 3), dtype=torch.int32, device=row_ptr.device)
+    count = torch.zeros(1, dtype=torch.int64, device=row_ptr.device)
+    _lib.call("shgo_b200_csr_edges3", _ptr(row_ptr), _ptr(col), n, _ptr(out), cap, _ptr(count), _stream())
+    return out[:cap]
+
+
+def row_present(row_ptr):
+    """uint8 [n]: 1 where the row is non-empty (the vertex exists in the reference's cache)"""
+    n = row_ptr.numel() - 1
+    out = torch.empty(n, dtype=torch.uint8, device=row_ptr.device)
+    _lib.call("shgo_b200_row_present", _ptr(row_ptr), n, _ptr(out), _stream())
+    return out
+
+
 def first_seen(simplices, n):
     """int64 [n]: position at which vf_to_vv first touches each vertex (-1 = never)."""
     assert simplices.dtype == torch.int32 and simplices.dim() == 2

@@ -73,6 +73,19 @@ def shgo_b200_csr_from_simplices(simplices, S, dp1, n, row_ptr, col, col_cap, nn
     _req(col or pairs == 0, "null col")
 
 
+def shgo_b200_csr_edges3(row_ptr, col, n, out, cap, count, stream):
+    _req(count, "null count")
+    if n == 0:
+        return
+    _req(row_ptr and (out or cap == 0), "null pointer")
+
+
+def shgo_b200_row_present(row_ptr, n, present, stream):
+    if n == 0:
+        return
+    _req(row_ptr and present, "null pointer")
+
+
 def shgo_b200_first_seen(simplices, S, dp1, n, first_seen, stream):
     _req(first_seen, "null output")
     _req(simplices or S == 0, "null simplices")

@@ -99,6 +99,18 @@ def pool_rank(pool, f, x_soa=None, xl=None, by="f", xref=None):
     return torch.from_numpy(np.ascontiguousarray(out))
 
 
+def csr_edges3(row_ptr, col):
+    rp, c = row_ptr.numpy(), col.numpy()
+    rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    keep = rows < c
+    return torch.from_numpy(np.stack([rows[keep], c[keep], c[keep]], 1).astype(np.int32))
+
+
+def row_present(row_ptr):
+    rp = row_ptr.numpy()
+    return torch.from_numpy((rp[1:] > rp[:-1]).astype(np.uint8))
+
+
 def count_nfev(row_ptr, feasible=None, out=None):
     c = orc.nfev(row_ptr.numpy(), None if feasible is None else feasible.numpy())
     return torch.tensor([int(c)], dtype=torch.int64)
@@ -283,7 +295,7 @@ def install(monkeypatch):
     """Patch shgo_b200.hotpath in place (functions are looked up as attributes at call time)."""
     from shgo_b200 import hotpath as hp
     for name in ("SobolTables", "sobol_points", "eval_sobol", "eval_points", "mask_infeasible",
-                 "csr_from_simplices", "sampling_subspace", "pool_rank", "count_nfev", "morton_order", "relabel3", "gather", "scatter_u8", "first_seen", "star_csr", "star_csr_shard", "PoolWorkspace", "compact_pool", "argmin", "lattice_eval",
+                 "csr_from_simplices", "csr_edges3", "row_present", "sampling_subspace", "pool_rank", "count_nfev", "morton_order", "relabel3", "gather", "scatter_u8", "first_seen", "star_csr", "star_csr_shard", "PoolWorkspace", "compact_pool", "argmin", "lattice_eval",
                  "lattice_coords", "lattice_star", "local_bounds_csr", "lattice_local_bounds", "lattice_eval_push"):
         obj = globals()[name]
         real = getattr(hp, name)

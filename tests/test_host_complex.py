@@ -295,3 +295,15 @@ def test_sampling_subspace_served_by_the_device(sb, monkeypatch):
     assert used
     assert (res.nfev, res.nit, res.success) == (ref.nfev, ref.nit, ref.success)
     np.testing.assert_allclose(res.x, ref.x, rtol=1e-9, atol=1e-12)
+
+
+def test_lattice_limits_fall_back_to_the_generator(sb):
+    """the closed-form lattice kernels take d <= 12 and < 2^32 vertices; beyond that the
+    complex must not enter lattice mode (the caller then replays the generator, like for artefact bounds)"""
+    from shgo_b200 import functors as F
+    from shgo_b200.complex import DeviceComplex
+    c13 = DeviceComplex(13, domain=[(-1.0, 1.0)] * 13, sfield=F.sphere)
+    assert c13._enter_lattice(0) is False and c13.mode is None
+    c12 = DeviceComplex(12, domain=[(-1.0, 1.0)] * 12, sfield=F.sphere)
+    assert c12._enter_lattice(3) is False          # (2^3+1)^12 + 2^36 vertices > 2^32
+    assert c12._enter_lattice(0) is True and c12.mode == "lattice"
