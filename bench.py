@@ -399,6 +399,10 @@ def main():
     marks = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    # one more untimed step right in front of the timed region, in stream order: its device-side barrier
+    # lines the ranks' streams up to within a few microseconds, where dist.barrier() + synchronize leave
+    # them up to ~0.5 ms apart (that skew would be charged to the first timed step of the early ranks)
+    step()
     t0.record(stream)
     for k in range(args.steps):
         marks[k][0].record(stream)
