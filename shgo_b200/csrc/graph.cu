@@ -196,26 +196,20 @@ rowptr_kernel(const uint32_t *__restrict__ deg, uint64_t n, const uint64_t *__re
 
 // =============================================================================================
 // K3: vf_to_vv (reference _complex.py:1053-1074).  Undirected edges among simplex slots 0,1,2
-// (dp1 >= 3) or the pair itself (dp1 == 2) are de-duplicated in an open-addressing hash set
-// (64-bit keys min<<32|max, linear probing, atomicCAS), degrees are counted on first insertion,
-// rows are filled by atomic cursors and finally rank-sorted, one warp per row, so that the CSR
-// is deterministic.
+// (dp1 >= 3) or the pair itself (dp1 == 2).  Round 2: a BUCKET build instead of a global hash set --
+//   count    every pair adds 1 to both endpoints' counters (duplicates included: an edge of a 2-D
+//            Delaunay mesh is seen by two triangles)
+//   scan     -> offsets of the duplicate-laden rows
+//   fill     every pair drops each endpoint into the other's row (atomic cursor per row)
+//   sort     every row is sorted and de-duplicated in place (a thread per row up to 32 entries, a CTA
+//            radix sort for hubs) -> degree
+//   scan + compact -> row_ptr, col (ascending, unique: deterministic whatever the atomics' order)
+// The atomics now hit n 4-byte counters (L2-resident for any mesh qhull can produce) instead of a
+// hash table of 2 x pairs 8-byte slots scattered over gigabytes: 2-D Delaunay of 2^24 points 21 -> ~3 ms.
 // =============================================================================================
-constexpr uint64_t kEmptyKey = ~0ull;
-
-__device__ __forceinline__ uint64_t mix64(uint64_t x)
-{
-    x ^= x >> 33;
-    x *= 0xff51afd7ed558ccdULL;
-    x ^= x >> 33;
-    x *= 0xc4ceb9fe1a85ec53ULL;
-    x ^= x >> 33;
-    return x;
-}
-
-__global__ void edge_insert_kernel(const int32_t *__restrict__ simplices, uint64_t S, int dp1,
-                                   uint64_t n, unsigned long long *__restrict__ table,
-                                   uint64_t mask, uint32_t *__restrict__ deg, int *__restrict__ bad)
+template <class Fn>
+__device__ __forceinline__ void for_each_pair(const int32_t *__restrict__ simplices, uint64_t S, int dp1, uint64_t n,
+                                              int *__restrict__ bad, Fn fn)
 {
     const int npair = dp1 >= 3 ? 3 : 1;
     for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < S;
@@ -226,27 +220,36 @@ __global__ void edge_insert_kernel(const int32_t *__restrict__ simplices, uint64
         v[1] = __ldg(sp + 1);
         v[2] = dp1 >= 3 ? __ldg(sp + 2) : 0;
         for (int e = 0; e < npair; ++e) {
-            int32_t a = v[e == 2 ? 1 : 0], b = v[e == 0 ? 1 : 2];
+            const int32_t a = v[e == 2 ? 1 : 0], b = v[e == 0 ? 1 : 2];
             if (a == b) continue;  // connect(): `v is not self` (_vertex.py:123)
             if ((uint32_t)a >= n || (uint32_t)b >= n) {
                 *bad = 1;
                 continue;
             }
-            uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
-            unsigned long long key = ((unsigned long long)lo << 32) | hi;
-            uint64_t h = mix64(key) & mask;
-            while (true) {
-                unsigned long long prev = atomicCAS(table + h, kEmptyKey, key);
-                if (prev == kEmptyKey) {
-                    atomicAdd(deg + lo, 1u);
-                    atomicAdd(deg + hi, 1u);
-                    break;
-                }
-                if (prev == key) break;
-                h = (h + 1) & mask;
-            }
+            fn((uint32_t)a, (uint32_t)b);
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+edge_count_kernel(const int32_t *__restrict__ simplices, uint64_t S, int dp1, uint64_t n,
+                  uint32_t *__restrict__ deg, int *__restrict__ bad)
+{
+    for_each_pair(simplices, S, dp1, n, bad, [&](uint32_t a, uint32_t b) {
+        atomicAdd(deg + a, 1u);
+        atomicAdd(deg + b, 1u);
+    });
+}
+
+__global__ void __launch_bounds__(256)
+edge_fill_kernel(const int32_t *__restrict__ simplices, uint64_t S, int dp1, uint64_t n,
+                 const int64_t *__restrict__ rp_dup, uint32_t *__restrict__ cursor, int32_t *__restrict__ rows,
+                 int *__restrict__ bad)
+{
+    for_each_pair(simplices, S, dp1, n, bad, [&](uint32_t a, uint32_t b) {
+        rows[rp_dup[a] + atomicAdd(cursor + a, 1u)] = (int32_t)b;
+        rows[rp_dup[b] + atomicAdd(cursor + b, 1u)] = (int32_t)a;
+    });
 }
 
 // order in which Complex.vf_to_vv first touches each vertex (simplex by simplex, slots 0,1,2):
@@ -271,50 +274,52 @@ __global__ void flag_bad_kernel(const int *__restrict__ bad, uint64_t *__restric
     if (*bad) *nnz = ~0ull;
 }
 
-__global__ void edge_fill_kernel(const unsigned long long *__restrict__ table, uint64_t slots,
-                                 const int64_t *__restrict__ row_ptr, uint32_t *__restrict__ cursor,
-                                 int32_t *__restrict__ col_tmp)
-{
-    for (uint64_t h = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; h < slots;
-         h += (uint64_t)gridDim.x * blockDim.x) {
-        unsigned long long key = table[h];
-        if (key == kEmptyKey) continue;
-        uint32_t lo = (uint32_t)(key >> 32), hi = (uint32_t)key;
-        col_tmp[row_ptr[lo] + atomicAdd(cursor + lo, 1u)] = (int32_t)hi;
-        col_tmp[row_ptr[hi] + atomicAdd(cursor + hi, 1u)] = (int32_t)lo;
-    }
-}
-
-// Rows are sorted ascending (entries of a row are distinct), col_tmp -> col, in two tiers:
-//   degree <= 32   one warp per row, rank by 32 shuffles (a Delaunay mesh in 2-D / 3-D is all of this)
-//   larger         listed, then one CTA per row: stable LSD radix sort, 8 bits per pass, ping-pong
-//                  between the row's slices of col_tmp and col -- O(deg) per pass instead of the
-//                  O(deg^2) rank sort of round 1 (a hub of 20 000 neighbours: 4e8 comparisons on 32 lanes)
+// Rows (with duplicates) are sorted ascending and de-duplicated IN PLACE; deg[r] = distinct entries.
+//   <= 32 entries  one thread per row: insertion sort in a private array, unique entries written back
+//   longer         listed, then one CTA per row: stable LSD radix sort (8 bits per pass, only the
+//                  passes the vertex count needs) ping-ponging between the row and a scratch row in
+//                  `col`, then a CTA-wide unique compaction back into the row -- O(len) per pass where
+//                  round 1 ranked with O(len^2) comparisons on one warp
 __global__ void __launch_bounds__(256)
-row_sort_small_kernel(const int64_t *__restrict__ row_ptr, uint64_t n, const int32_t *__restrict__ col_tmp,
-                      int32_t *__restrict__ col, uint32_t *__restrict__ big_list, int *__restrict__ big_count)
+row_sort_small_kernel(const int64_t *__restrict__ rp_dup, uint64_t n, int32_t *__restrict__ rows,
+                      uint32_t *__restrict__ deg, uint32_t *__restrict__ big_list, int *__restrict__ big_count)
 {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
-        const int64_t b = row_ptr[r], e = row_ptr[r + 1];
-        const int64_t len = e - b;
-        if (len == 0) continue;
-        if (len > 32) {
-            if (lane == 0) big_list[atomicAdd(big_count, 1)] = (uint32_t)r;
+    // one THREAD per row: a mesh row has ~12 entries (duplicates included); a warp per row spent 32
+    // shuffle steps on it whatever its length (7.2 of the 12 ms of a 2^24-vertex build, ncu)
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n;
+         r += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t b = rp_dup[r];
+        const int len = (int)min((int64_t)33, rp_dup[r + 1] - b);
+        if (len == 0) {
+            deg[r] = 0;
             continue;
         }
-        const int32_t v = lane < len ? col_tmp[b + lane] : 0x7fffffff;
-        int rank = 0;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) rank += __shfl_sync(0xffffffffu, v, k) < v;
-        if (lane < len) col[b + rank] = v;
+        if (len > 32) {
+            big_list[atomicAdd(big_count, 1)] = (uint32_t)r;
+            continue;
+        }
+        int32_t v[32];
+        for (int i = 0; i < len; ++i) v[i] = rows[b + i];
+        for (int i = 1; i < len; ++i) {  // insertion sort
+            const int32_t x = v[i];
+            int j = i - 1;
+            while (j >= 0 && v[j] > x) {
+                v[j + 1] = v[j];
+                --j;
+            }
+            v[j + 1] = x;
+        }
+        int m = 0;
+        for (int i = 0; i < len; ++i)
+            if (i == 0 || v[i] != v[i - 1]) rows[b + m++] = v[i];
+        deg[r] = (uint32_t)m;
     }
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-row_sort_big_kernel(const int64_t *__restrict__ row_ptr, int32_t *__restrict__ col_tmp, int32_t *__restrict__ col,
-                    const uint32_t *__restrict__ big_list, const int *__restrict__ big_count, int npass)
+row_sort_big_kernel(const int64_t *__restrict__ rp_dup, int32_t *__restrict__ rows, int32_t *__restrict__ scratch,
+                    uint32_t *__restrict__ deg, const uint32_t *__restrict__ big_list,
+                    const int *__restrict__ big_count, int npass)
 {
     __shared__ uint32_t hist[256], base[256], running[256];
     __shared__ uint32_t cnt[kScanThreads / 32][256];
@@ -322,9 +327,9 @@ row_sort_big_kernel(const int64_t *__restrict__ row_ptr, int32_t *__restrict__ c
     const int nbig = *big_count;
     for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
         const uint32_t r = big_list[q];
-        const int64_t b = row_ptr[r];
-        const uint32_t len = (uint32_t)(row_ptr[r + 1] - b);
-        uint32_t *A = reinterpret_cast<uint32_t *>(col_tmp + b), *B = reinterpret_cast<uint32_t *>(col + b);
+        const int64_t b = rp_dup[r];
+        const uint32_t len = (uint32_t)(rp_dup[r + 1] - b);
+        uint32_t *A = reinterpret_cast<uint32_t *>(rows + b), *B = reinterpret_cast<uint32_t *>(scratch + b);
         for (int p = 0; p < npass; ++p) {
             const uint32_t *in = (p & 1) ? B : A;
             uint32_t *out = (p & 1) ? A : B;
@@ -365,9 +370,41 @@ row_sort_big_kernel(const int64_t *__restrict__ row_ptr, int32_t *__restrict__ c
                 __syncthreads();
             }
         }
-        if ((npass & 1) == 0)  // an even number of passes ends in col_tmp
+        // the sorted row sits in B after an odd number of passes, else in A; unique entries go to the
+        // start of A (through B when the sorted row is in A: in-place compaction would race)
+        uint32_t *src = (npass & 1) ? B : A;
+        if (!(npass & 1)) {
             for (uint32_t i = t; i < len; i += kScanThreads) B[i] = A[i];
+            __syncthreads();
+            src = B;
+        }
+        uint32_t run = 0;
+        for (uint32_t r0 = 0; r0 < len; r0 += kScanThreads) {
+            const uint32_t i = r0 + t;
+            const bool live = i < len;
+            const uint32_t v = live ? src[i] : 0u;
+            const bool uniq = live && (i == 0 || v != src[i - 1]);
+            uint32_t total;
+            const uint32_t ex = block_exclusive_scan(uniq ? 1u : 0u, &total);
+            if (uniq) A[run + ex] = v;
+            run += total;
+        }
+        if (t == 0) deg[r] = run;
         __syncthreads();
+    }
+}
+
+// final CSR: row r = the first deg[r] entries of its duplicate-laden row (a thread per row; long rows
+// are rare and only cost their own thread)
+__global__ void __launch_bounds__(256)
+row_compact_kernel(const int64_t *__restrict__ rp_dup, const int32_t *__restrict__ rows,
+                   const int64_t *__restrict__ row_ptr, uint64_t n, int32_t *__restrict__ col)
+{
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n;
+         r += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t src = rp_dup[r], dst = row_ptr[r];
+        const int64_t len = row_ptr[r + 1] - dst;
+        for (int64_t i = 0; i < len; ++i) col[dst + i] = rows[src + i];
     }
 }
 
@@ -492,12 +529,6 @@ nfev_kernel(const int64_t *__restrict__ row_ptr, const uint8_t *__restrict__ fea
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
 
-static inline uint64_t next_pow2(uint64_t x)
-{
-    uint64_t p = 1;
-    while (p < x) p <<= 1;
-    return p;
-}
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static inline unsigned grid_for(uint64_t items, int threads, int per_sm)
 {
@@ -596,11 +627,11 @@ int shgo_b200_compact_pool(const uint8_t *is_min, uint64_t n, int64_t base, int6
 
 size_t shgo_b200_csr_workspace(uint64_t S, int dp1, uint64_t n)
 {
-    uint64_t pairs = dp1 >= 3 ? 3 * S : S;
-    uint64_t slots = next_pow2(pairs * 2 < 64 ? 64 : pairs * 2);
-    uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
-    return align256(slots * 8) + 2 * align256(n * 4) + align256(pairs * 2 * 4 + 16) +
-           align256((nb + 2) * 8) + align256(16);
+    const uint64_t pairs = dp1 >= 3 ? 3 * S : S;
+    const uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
+    // duplicate-laden rows, their offsets, degree + cursor / long-row list, block sums, flags
+    return align256(pairs * 2 * 4 + 16) + align256((n + 1) * 8) + 2 * align256(n * 4) + align256((nb + 2) * 8) +
+           align256(16);
 }
 
 int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, uint64_t n,
@@ -619,39 +650,42 @@ int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, 
         return fail(SHGO_B200_ERR_WORKSPACE, "csr workspace: need %zu bytes, got %zu",
                     shgo_b200_csr_workspace(S, dp1, n), tmp_bytes);
     cudaStream_t st = as_stream(stream);
-    const uint64_t slots = next_pow2(pairs * 2 < 64 ? 64 : pairs * 2);
     const uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
     unsigned char *p = static_cast<unsigned char *>(tmp);
-    unsigned long long *table = reinterpret_cast<unsigned long long *>(p);
-    p += align256(slots * 8);
+    int32_t *rows = reinterpret_cast<int32_t *>(p);
+    p += align256(pairs * 2 * 4 + 16);
+    int64_t *rp_dup = reinterpret_cast<int64_t *>(p);
+    p += align256((n + 1) * 8);
     uint32_t *deg = reinterpret_cast<uint32_t *>(p);
     p += align256(n * 4);
-    uint32_t *cursor = reinterpret_cast<uint32_t *>(p);
+    uint32_t *cursor = reinterpret_cast<uint32_t *>(p);  // fill cursors, then the list of long rows
     p += align256(n * 4);
-    int32_t *col_tmp = reinterpret_cast<int32_t *>(p);
-    p += align256(pairs * 2 * 4 + 16);
     uint64_t *sums = reinterpret_cast<uint64_t *>(p);
     p += align256((nb + 2) * 8);
-    int *bad = reinterpret_cast<int *>(p);
+    int *bad = reinterpret_cast<int *>(p);  // [0] out-of-range vertex seen, [1] number of long rows
 
-    SHGO_CUDA_TRY(cudaMemsetAsync(table, 0xff, slots * 8, st));
     SHGO_CUDA_TRY(cudaMemsetAsync(deg, 0, align256(n * 4) * 2, st));  // deg + cursor
-    SHGO_CUDA_TRY(cudaMemsetAsync(bad, 0, 2 * sizeof(int), st));  // bad flag, number of long rows
-    if (S > 0)
-        edge_insert_kernel<<<grid_for(S, 256, 8), 256, 0, st>>>(simplices, S, dp1, n, table, slots - 1,
-                                                                deg, bad);
+    SHGO_CUDA_TRY(cudaMemsetAsync(bad, 0, 2 * sizeof(int), st));
+    const unsigned rows_grid = (unsigned)(n / kScanBlock + 1);  // n+1 outputs
+    if (S > 0) edge_count_kernel<<<grid_for(S, 256, 8), 256, 0, st>>>(simplices, S, dp1, n, deg, bad);
     block_sum_kernel<uint32_t><<<(unsigned)nb, kScanThreads, 0, st>>>(deg, n, sums, 0);
     scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, nnz);
-    // n+1 outputs: one more block when n is a multiple of the block size
-    rowptr_kernel<<<(unsigned)(n / kScanBlock + 1), kScanThreads, 0, st>>>(deg, n, sums, row_ptr);
+    rowptr_kernel<<<rows_grid, kScanThreads, 0, st>>>(deg, n, sums, rp_dup);
     if (S > 0) {
-        edge_fill_kernel<<<grid_for(slots, 256, 8), 256, 0, st>>>(table, slots, row_ptr, cursor, col_tmp);
-        // `cursor` is free after the fill: it takes the list of rows longer than a warp
-        row_sort_small_kernel<<<grid_for(n * 32, 256, 8), 256, 0, st>>>(row_ptr, n, col_tmp, col, cursor, bad + 1);
+        edge_fill_kernel<<<grid_for(S, 256, 8), 256, 0, st>>>(simplices, S, dp1, n, rp_dup, cursor, rows, bad);
+        // `cursor` is free after the fill: it takes the list of rows longer than a warp; deg becomes
+        // the number of DISTINCT entries
+        row_sort_small_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(rp_dup, n, rows, deg, cursor, bad + 1);
         int npass = 1;
         while (npass < 4 && (n - 1) >> (8 * npass)) ++npass;  // vertex ids < n: skip all-zero digits
-        row_sort_big_kernel<<<(unsigned)sm_count() * 4, kScanThreads, 0, st>>>(row_ptr, col_tmp, col, cursor, bad + 1,
+        row_sort_big_kernel<<<(unsigned)sm_count() * 4, kScanThreads, 0, st>>>(rp_dup, rows, col, deg, cursor, bad + 1,
                                                                              npass);
+    }
+    block_sum_kernel<uint32_t><<<(unsigned)nb, kScanThreads, 0, st>>>(deg, n, sums, 0);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(sums, nb, nnz);
+    rowptr_kernel<<<rows_grid, kScanThreads, 0, st>>>(deg, n, sums, row_ptr);
+    if (S > 0) {
+        row_compact_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(rp_dup, rows, row_ptr, n, col);
         flag_bad_kernel<<<1, 1, 0, st>>>(bad, nnz);
     }
     SHGO_CUDA_TRY(cudaGetLastError());
