@@ -39,7 +39,7 @@ sha=hashlib.sha256(open("shgo_b200/csrc/star.cu","rb").read()).hexdigest()[:16]
 json.dump({"log2n":28,"n_gpus":1,"dram_bytes_read":rdb,"dram_bytes_write":wrb,"kernel":m["Kernel Name"][0],"star_cu_sha16":sha,
            "duration_ms_under_ncu":float(m["gpu__time_duration.sum"][0]),
            "source":"profiles/r2_kernels.md (ncu --set full of tools/star_variants.py --one 28, round 2)"}, open("profiles/r2_star_traffic.json","w"), indent=1)
-for fn,title,npts,d in (("rastrigin","Rastrigin 6-D, Sobol n = 2^26 (config 2's objective)",2**26,6),("ackley","Ackley 10-D, Sobol n = 2^26 (config 3's objective)",2**26,10),("cattle","cattle-feed 4-D with g1, g2, Sobol n = 2^26 (config 4)",2**26,4),("st","Styblinski-Tang 8-D, Sobol n = 2^28 (config 5; capture taken before the single-rounding fast path: 0.967 ms -> 0.885 ms after)",2**28,8)):
+for fn,title,npts,d in (("rastrigin","Rastrigin 6-D, Sobol n = 2^26 (config 2's objective)",2**26,6),("ackley","Ackley 10-D, Sobol n = 2^26 (config 3's objective)",2**26,10),("cattle","cattle-feed 4-D with g1, g2, Sobol n = 2^26 (config 4)",2**26,4),("st","Styblinski-Tang 8-D, Sobol n = 2^26 (config 5's objective)",2**26,8)):
     rep="gpurun_out/r2_eval_%s.ncu-rep" % fn
     t,m=table(rep,"eval_kernel: "+title); out.append("\n"+t)
     tot,mix=sass_mix(rep)
