@@ -276,7 +276,8 @@ __global__ void flag_bad_kernel(const int *__restrict__ bad, uint64_t *__restric
 
 // Rows (with duplicates) are sorted ascending and de-duplicated IN PLACE; deg[r] = distinct entries.
 //   <= 32 entries  one thread per row: insertion sort in a private array, unique entries written back
-//   longer         listed, then one CTA per row: stable LSD radix sort (8 bits per pass, only the
+//   33 .. 1024     listed, then one warp per row: bitonic sort in shared memory (row_sort_warp_kernel)
+//   longer (hubs)  listed again, then one CTA per row: stable LSD radix sort (8 bits per pass, only the
 //                  passes the vertex count needs) ping-ponging between the row and a scratch row in
 //                  `col`, then a CTA-wide unique compaction back into the row -- O(len) per pass where
 //                  round 1 ranked with O(len^2) comparisons on one warp
@@ -313,6 +314,60 @@ row_sort_small_kernel(const int64_t *__restrict__ rp_dup, uint64_t n, int32_t *_
         for (int i = 0; i < len; ++i)
             if (i == 0 || v[i] != v[i - 1]) rows[b + m++] = v[i];
         deg[r] = (uint32_t)m;
+    }
+}
+
+// rows of 33 .. kWarpRowMax entries (the dup-laden rows of 3-D and higher meshes: a vertex sits in
+// dozens of simplices): one WARP per listed row, bitonic sort in a shared-memory line, unique entries
+// compacted with ballots; longer rows are passed on to the CTA radix sort
+constexpr int kWarpRowMax = 1024;
+__global__ void __launch_bounds__(256)
+row_sort_warp_kernel(const int64_t *__restrict__ rp_dup, int32_t *__restrict__ rows, uint32_t *__restrict__ deg,
+                     const uint32_t *__restrict__ big_list, const int *__restrict__ big_count,
+                     uint32_t *__restrict__ huge_list, int *__restrict__ huge_count)
+{
+    __shared__ int32_t line[8][kWarpRowMax];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    int32_t *sm = line[wl];
+    const int nbig = *big_count;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nbig; q += warps) {
+        const uint32_t r = big_list[q];
+        const int64_t b = rp_dup[r];
+        const int64_t len64 = rp_dup[r + 1] - b;
+        if (len64 > kWarpRowMax) {
+            if (lane == 0) huge_list[atomicAdd(huge_count, 1)] = r;
+            continue;
+        }
+        const int len = (int)len64;
+        int N = 64;
+        while (N < len) N <<= 1;
+        for (int i = lane; i < N; i += 32) sm[i] = i < len ? rows[b + i] : 0x7fffffff;
+        __syncwarp();
+        for (int k = 2; k <= N; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = lane; i < N; i += 32) {
+                    const int x = i ^ j;
+                    if (x > i) {
+                        const int32_t va = sm[i], vb = sm[x];
+                        if ((va > vb) == ((i & k) == 0)) {
+                            sm[i] = vb;
+                            sm[x] = va;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        int run = 0;
+        for (int i0 = 0; i0 < len; i0 += 32) {
+            const int i = i0 + lane;
+            const bool uniq = i < len && (i == 0 || sm[i] != sm[i - 1]);
+            const unsigned m = __ballot_sync(0xffffffffu, uniq);
+            if (uniq) rows[b + run + __popc(m & ((1u << lane) - 1u))] = sm[i];
+            run += __popc(m);
+        }
+        if (lane == 0) deg[r] = (uint32_t)run;
+        __syncwarp();
     }
 }
 
@@ -631,7 +686,7 @@ size_t shgo_b200_csr_workspace(uint64_t S, int dp1, uint64_t n)
     const uint64_t nb = (n + kScanBlock - 1) / kScanBlock;
     // duplicate-laden rows, their offsets, degree + cursor / long-row list, block sums, flags
     return align256(pairs * 2 * 4 + 16) + align256((n + 1) * 8) + 2 * align256(n * 4) + align256((nb + 2) * 8) +
-           align256(16);
+           align256((pairs * 2 / kWarpRowMax + 64) * 4) + align256(16);
 }
 
 int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, uint64_t n,
@@ -662,10 +717,12 @@ int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, 
     p += align256(n * 4);
     uint64_t *sums = reinterpret_cast<uint64_t *>(p);
     p += align256((nb + 2) * 8);
-    int *bad = reinterpret_cast<int *>(p);  // [0] out-of-range vertex seen, [1] number of long rows
+    uint32_t *huge = reinterpret_cast<uint32_t *>(p);  // rows longer than kWarpRowMax (at most 2 pairs / 1024)
+    p += align256((pairs * 2 / kWarpRowMax + 64) * 4);
+    int *bad = reinterpret_cast<int *>(p);  // [0] out-of-range vertex seen, [1] rows > 32, [2] rows > kWarpRowMax
 
     SHGO_CUDA_TRY(cudaMemsetAsync(deg, 0, align256(n * 4) * 2, st));  // deg + cursor
-    SHGO_CUDA_TRY(cudaMemsetAsync(bad, 0, 2 * sizeof(int), st));
+    SHGO_CUDA_TRY(cudaMemsetAsync(bad, 0, 3 * sizeof(int), st));
     const unsigned rows_grid = (unsigned)(n / kScanBlock + 1);  // n+1 outputs
     if (S > 0) edge_count_kernel<<<grid_for(S, 256, 8), 256, 0, st>>>(simplices, S, dp1, n, deg, bad);
     block_sum_kernel<uint32_t><<<(unsigned)nb, kScanThreads, 0, st>>>(deg, n, sums, 0);
@@ -678,7 +735,8 @@ int shgo_b200_csr_from_simplices(const int32_t *simplices, uint64_t S, int dp1, 
         row_sort_small_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(rp_dup, n, rows, deg, cursor, bad + 1);
         int npass = 1;
         while (npass < 4 && (n - 1) >> (8 * npass)) ++npass;  // vertex ids < n: skip all-zero digits
-        row_sort_big_kernel<<<(unsigned)sm_count() * 4, kScanThreads, 0, st>>>(rp_dup, rows, col, deg, cursor, bad + 1,
+        row_sort_warp_kernel<<<(unsigned)sm_count() * 4, 256, 0, st>>>(rp_dup, rows, deg, cursor, bad + 1, huge, bad + 2);
+        row_sort_big_kernel<<<(unsigned)sm_count() * 2, kScanThreads, 0, st>>>(rp_dup, rows, col, deg, huge, bad + 2,
                                                                              npass);
     }
     block_sum_kernel<uint32_t><<<(unsigned)nb, kScanThreads, 0, st>>>(deg, n, sums, 0);
