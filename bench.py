@@ -181,13 +181,27 @@ def reference_arm(args):
     }))
 
 
+EXCHANGES = {
+    "fused": "none: f shards peer-mapped over NVLink (CUDA IPC); the star kernel reads its candidates' remote "
+             "neighbours in place, inline, once the owner has published its shard; 1 stream-ordered barrier per step",
+    "p2p": "none: f shards peer-mapped over NVLink (CUDA IPC), the candidates' remote neighbour values read in place "
+           "by a second kernel, pre-filtered by group minima pushed in bulk; 1 stream-ordered barrier per step",
+    "allgather": "nccl all_gather of f", "none": "none"}
+
+
 def config_of(args):
-    """identical in both arms: the workload, and the size both the CPU arm and the e2e leg run"""
-    return {"workload": workload_name(args.log2n), "points": 1 << args.log2n,
+    """Identical in both arms by construction (everything comes from the command line): the workload, the
+    size both the CPU arm and the e2e leg run, and how the GPU arm treats L2 and the exchange."""
+    n, world = 1 << args.log2n, max(args.gpus, 1)
+    return {"workload": workload_name(args.log2n), "points": n,
             "e2e_and_cpu_points": 1 << min(args.e2e_log2n, args.log2n),
             "note": "value: device-resident 2^%d points; e2e (host buffers through the C ABI) and the CPU arm both "
                     "run the same problem at 2^%d points (degree-%d hypercube graph): the host CSR of the full "
-                    "size is 32 GB" % (args.log2n, min(args.e2e_log2n, args.log2n), min(args.e2e_log2n, args.log2n))}
+                    "size is 32 GB" % (args.log2n, min(args.e2e_log2n, args.log2n), min(args.e2e_log2n, args.log2n)),
+            "rows_per_gpu": n // world,
+            "l2": "inputs (col = %.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
+                  % (n // world * args.log2n * 4 / 1e9),
+            "exchange": EXCHANGES[args.exchange if world > 1 else "none"]}
 
 
 def workload_name(log2n):
@@ -543,16 +557,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": dict(config_of(args), rows_per_gpu=rows,
-                       l2="inputs (col = %.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
-                          % (nnz_l * 4 / 1e9),
-                       exchange={"fused": "none: f shards peer-mapped over NVLink (CUDA IPC); the star kernel "
-                                          "reads its candidates' remote neighbours in place, inline, once the "
-                                          "owner has published its shard; 1 stream-ordered barrier per step",
-                                 "p2p": "none: f shards peer-mapped over NVLink (CUDA IPC), neighbour "
-                                        "values read in place by a second kernel; 1 stream-ordered "
-                                        "barrier per step", "allgather": "nccl all_gather of f",
-                                 "none": "none"}[it.exchange]),
+        "config": config_of(args),
         "roofline": {"bound": "hbm", "kernel": "star_kernel (csrc/star.cu)", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
