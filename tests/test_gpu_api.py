@@ -150,3 +150,30 @@ def test_local_bounds_through_the_driver_seam(sb, kw):
     finally:
         api.uninstall()
 
+
+
+def test_large_mesh_goes_through_the_z_order_numbering_and_device_pool_ranking(sb, monkeypatch):
+    """A mesh of >= 2^15 vertices is classified in Z-order numbering (complex.MORTON_MIN_VERTICES) and a pool of
+    >= DEVICE_POOL_RANK_MIN vertices is filtered / ranked on the device: the driver must see the same complex as
+    with both switched off -- same vertex count, nfev, pool (coordinates, in order) and lowest vertex."""
+    from shgo_b200 import api, complex as cx, functors as F
+    bounds = [(-5.12, 4.7), (-4.9, 5.12)]
+    kw = dict(n=1 << 15, iters=1, sampling_method="sobol")
+
+    def run(morton_min, rank_min):
+        monkeypatch.setattr(cx, "MORTON_MIN_VERTICES", morton_min)
+        monkeypatch.setattr(api, "DEVICE_POOL_RANK_MIN", rank_min)
+        s = sb.SHGO(F.rastrigin, bounds, **kw)
+        s.iterate_complex()
+        s.minimizers()
+        return s
+
+    a = run(1 << 40, 1 << 40)            # both off
+    b = run(1 << 15, 16)                 # both on
+    assert a.HC._morton is None and b.HC._morton is not None
+    assert a.HC.V.size() == b.HC.V.size() and a.HC.V.nfev == b.HC.V.nfev
+    assert np.array_equal(a.HC.pool_indices, b.HC.pool_indices) and len(a.HC.pool_indices) > 64
+    assert a.HC.argmin_index == b.HC.argmin_index
+    assert np.array_equal(a.X_min, b.X_min)
+    assert np.array_equal(a.minimizer_pool_F, b.minimizer_pool_F)
+    assert [v.x for v in a.minimizer_pool] == [v.x for v in b.minimizer_pool]
