@@ -14,9 +14,12 @@
 //           On a random field a row survives k neighbours with probability 1/(k+1): 1 lane in 13 is
 //           still alive after this.
 //   funnel  the survivors are finished by the WHOLE warp: their remaining neighbours are dealt out to
-//           groups of lanes (1 survivor: 32 lanes, 2: 16 each, 3-4: 8 each, more: 4 each), one gather
-//           per lane, one ballot per step -- 32 gathers in flight per instruction instead of 2-3 live
-//           lanes dragging 16-wide rounds (round 1's kernel: 30 % of its stall samples).
+//           groups of lanes (up to 4 survivors: 8 lanes each, more: 4 each), one gather per lane, one
+//           ballot per step -- up to 32 gathers in flight per instruction instead of 2-3 live lanes
+//           dragging 16-wide rounds (round 1's kernel: 30 % of its stall samples).  Wider groups (16 / 32
+//           lanes for 2 / 1 survivors) are compiled in (MAXLG) but measured slower on the bench graph:
+//           8 neighbours per step test the near ones first and spare the row that fails there its
+//           far gathers, each a 64-byte DRAM fill (7.40 -> 7.20 ms at 2^28).
 //   remote  (sharded, FUSED) rows that passed every local neighbour and have neighbours on other GPUs
 //           read those f values in place over NVLink (peer-mapped shards) from inside this kernel, as
 //           soon as the owning GPU has published "my shard is written" (a flag per peer).  The loads
@@ -720,7 +723,7 @@ struct StarVariant {
 static StarVariant star_variant()
 {
     static StarVariant v = [] {
-        StarVariant d{2, 0, 4};
+        StarVariant d{2, 0, 3};  // bulk single-buffered staging, at most 8 lanes per funnel survivor
         if (const char *s = getenv("SHGO_B200_STAR")) {
             int a = d.bulk, b = d.warps, c = d.maxlg;
             sscanf(s, "%d,%d,%d", &a, &b, &c);

@@ -39,6 +39,18 @@ def one(log2n):
     pool = int(is_min.sum())
     fc = torch.zeros(n, dtype=torch.float64, device=dev)
     ms_c = timeit(lambda: hp.star_csr(row_ptr, col, fc, is_min=is_min))
+    if os.environ.get("STAR_EXTRA"):
+        from shgo_b200 import functors as F
+        feas = torch.ones(n, dtype=torch.uint8, device=dev)
+        nf = torch.zeros(1, dtype=torch.int64, device=dev)
+        ms_nf = timeit(lambda: hp.star_csr(row_ptr, col, f, is_min=is_min, feasible=feas, nfev=nf))
+        tab = hp.SobolTables([(-5.0, 5.0)] * 8)
+        fst, _ = hp.eval_sobol(F.F_STYBLINSKI_TANG, 0, tab, 0, n)
+        ms_st = timeit(lambda: hp.star_csr(row_ptr, col, fst, is_min=is_min))
+        pool_st = int(is_min.sum())
+        ms_st_nf = timeit(lambda: hp.star_csr(row_ptr, col, fst, is_min=is_min, feasible=feas, nfev=nf))
+        print("   extra: random f + nfev %.3f ms | Styblinski-Tang of Sobol points %.3f ms (pool %d) | + nfev %.3f ms"
+              % (ms_nf, ms_st, pool_st, ms_st_nf), flush=True)
     print("variant %-10s 2^%d  random f %7.3f ms %6.0f GB/s (%.3f of 6541)   constant f %7.3f ms %6.0f GB/s   pool %d"
           % (os.environ.get("SHGO_B200_STAR", "default"), log2n, ms, alg / ms / 1e6, alg / ms / 1e6 / 6541.1,
              ms_c, alg / ms_c / 1e6, pool), flush=True)
